@@ -1,0 +1,168 @@
+/* pda_b200.h -- C ABI of libpda_b200.so: the B200 (sm_100a) implementation of the
+ * probabilistic data-association hot path of EladMichael/probabilisticSemSlam.
+ *
+ * The reference has no FFI layer of its own: its boundary for this path is three C++
+ * headers (shortestPathCPP.hpp, assignment.h, nwPerm.h).  This file is the flat,
+ * batch-oriented C door underneath them; include/shortestPathCPP.hpp,
+ * include/assignment.h and include/nwPerm.h in this repository re-state the
+ * reference's C++ signatures on top of it (batch of one), see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every matrix is column-major double, C[row + col*numRow], rows = landmarks
+ *     followed by one dummy row per detection, columns = detections
+ *     (reference: assignment.cpp:705-722); numRow >= numCol (shortestPathCPP.hpp:156-157).
+ *   - index outputs are int64 (the reference's ptrdiff_t); -1 = unassigned.
+ *   - functions without the _host suffix take DEVICE pointers, enqueue on `stream`
+ *     (a cudaStream_t passed as void*, NULL = default stream) and do not synchronise.
+ *   - *_host functions take HOST pointers, copy in, run, copy out and synchronise.
+ *   - the caller owns every buffer, including the scratch `workspace`.
+ *   - return value: PDA_OK (0) or a negative PDA_ERR_*; pda_last_error() describes it.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point
+ *     returns PDA_ERR_CUDA.
+ */
+#ifndef PDA_B200_H
+#define PDA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDA_OK 0
+#define PDA_ERR_INVALID (-1)     /* bad argument (NULL, negative size, numRow < numCol, ...) */
+#define PDA_ERR_CUDA (-2)        /* CUDA runtime error or no device */
+#define PDA_ERR_UNSUPPORTED (-3) /* dimension above PDA_MAX_DIM / PDA_MAX_PERM_DIM */
+#define PDA_ERR_WORKSPACE (-4)   /* workspace too small for even one resident problem */
+
+#define PDA_MAX_DIM 128     /* largest numRow the Murty kernels take */
+#define PDA_MAX_PERM_DIM 32 /* largest permanent dimension (reference: nwPerm.cpp:265, 329) */
+
+/* cutMode of pda_murty_batch */
+#define PDA_CUT_NONE 0     /* kBest2D                      (shortestPathCPP.cpp:571-644) */
+#define PDA_CUT_RELATIVE 1 /* kBest2DCutoff(..., cutoff)   (shortestPathCPP.cpp:646-733) */
+#define PDA_CUT_STICKY 2   /* kBest2D on a ScratchSpace whose toCut/cutoffGain/maximize were left set by
+                              an earlier kBest2DCutoff (hpp:84-86, 130-132): children are still pruned
+                              against the absolute, shifted `cutoff`, in the sense of `cutMaximize` */
+
+/* weightMode of pda_murty_batch */
+#define PDA_WEIGHTS_NONE 0
+#define PDA_WEIGHTS_GATED 1   /* assignmentProb  (assignment.cpp:547-683): terms within 42 of the best */
+#define PDA_WEIGHTS_UNGATED 2 /* bruteForceProb  (assignment.cpp:910-945): every enumerated term */
+
+int pda_version(void);
+const char* pda_last_error(void);
+int pda_device_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Murty k-best enumeration (+ optional fused association weights), one warp per problem.
+ * Replaces kBest2D / kBest2DCutoff (shortestPathCPP.hpp:204-212, 256-265) and, with
+ * weightMode != 0, the marginalisation tail of assignmentProb / bruteForceProb.
+ *
+ *   costs, costOff[p]   problem p's numRow[p] x numCol[p] matrix starts at costs + costOff[p]
+ *   k                   hypotheses requested per problem
+ *   row4colBest         problem p, hypothesis i at row4colBest + r4cOff[p] + i*numCol[p]   (may be NULL)
+ *   col4rowBest         problem p, hypothesis i at col4rowBest + c4rOff[p] + i*numRow[p]   (may be NULL)
+ *   gainBest            problem p, hypothesis i at gainBest[p*k + i]                       (may be NULL)
+ *   nFound[p]           number of hypotheses found, 0 = infeasible (the reference's return value)
+ *   probs, probOff, nL  weightMode != 0: numCol[p] x (nL[p]+1) row-major table at probs + probOff[p]
+ *   workspace           >= pda_murty_workspace_bytes(...) gives full occupancy; smaller is legal
+ *                       (fewer problems in flight) down to one problem's worth
+ * Bit-exactness: row4col, col4row, enumeration order and gains are bit-identical to an
+ * IEEE-strict build of the reference (same operand order, same tie-breaks, same heap mechanics).
+ */
+int64_t pda_murty_workspace_bytes(int64_t nProblems, int32_t k, int32_t maxNumRow, int32_t maxNumCol);
+
+int pda_murty_batch(const double* costs, const int64_t* costOff, const int32_t* numRow, const int32_t* numCol,
+                    int64_t nProblems, int32_t maxNumRow, int32_t maxNumCol,
+                    int32_t k, int32_t cutMode, double cutoff, int32_t maximize, int32_t cutMaximize,
+                    int64_t* row4colBest, const int64_t* r4cOff,
+                    int64_t* col4rowBest, const int64_t* c4rOff,
+                    double* gainBest, int32_t* nFound,
+                    int32_t weightMode, double* probs, const int64_t* probOff, const int32_t* nL,
+                    void* workspace, int64_t workspaceBytes, void* stream);
+
+/* Same, HOST pointers; allocates and frees its own device buffers on `device`. */
+int pda_murty_batch_host(const double* costs, const int64_t* costOff, const int32_t* numRow, const int32_t* numCol,
+                         int64_t nProblems, int32_t k, int32_t cutMode, double cutoff, int32_t maximize,
+                         int32_t cutMaximize,
+                         int64_t* row4colBest, const int64_t* r4cOff,
+                         int64_t* col4rowBest, const int64_t* c4rOff,
+                         double* gainBest, int32_t* nFound,
+                         int32_t weightMode, double* probs, const int64_t* probOff, const int32_t* nL,
+                         int32_t device);
+
+/* Single LAP on a rectangular matrix without padding: assign2D (shortestPathCPP.hpp:144-149) when
+ * makeSafe != 0, shortestPathCPP (hpp:178-182) on an already-safe matrix otherwise.
+ * Per problem p: col4row[rowOff.. +numRow], row4col[colOff.. +numCol], u[colOff..], v[rowOff..],
+ * forbidden[rowOff..] (bytes), gain[p], feasible[p] (1 solved, 0 infeasible).
+ * rowOff/colOff are prefix sums of numRow/numCol.  Any output pointer may be NULL. */
+int pda_lap_batch(const double* costs, const int64_t* costOff, const int32_t* numRow, const int32_t* numCol,
+                  const int32_t* numCol4Gain, int64_t nProblems, int32_t maxNumRow, int32_t maxNumCol,
+                  int32_t makeSafe, int32_t maximize,
+                  const int64_t* rowOff, const int64_t* colOff,
+                  int64_t* col4row, int64_t* row4col, double* u, double* v, uint8_t* forbidden,
+                  double* gain, int32_t* feasible, void* stream);
+int pda_lap_batch_host(const double* costs, const int64_t* costOff, const int32_t* numRow, const int32_t* numCol,
+                       const int32_t* numCol4Gain, int64_t nProblems, int32_t makeSafe, int32_t maximize,
+                       const int64_t* rowOff, const int64_t* colOff,
+                       int64_t* col4row, int64_t* row4col, double* u, double* v, uint8_t* forbidden,
+                       double* gain, int32_t* feasible, int32_t device);
+
+/* ------------------------------------------------------------------------------------------
+ * Cost conditioning and element-wise likelihoods.
+ * conditionCosts (assignment.cpp:439-525): outCosts at costOff[p] (compacted goodRows[p] x numCol[p]),
+ * rowIdx at rowOff[p] (first goodRows[p] entries valid).  toProbs (assignment.cpp:527-542) in place.
+ */
+int pda_condition_costs_batch(const double* costs, const int64_t* costOff, const int32_t* numRow,
+                              const int32_t* numCol, int64_t nProblems, const int64_t* rowOff,
+                              double* outCosts, int64_t* rowIdx, int32_t* goodRows, void* stream);
+int pda_condition_costs_batch_host(const double* costs, const int64_t* costOff, const int32_t* numRow,
+                                   const int32_t* numCol, int64_t nProblems, const int64_t* rowOff,
+                                   double* outCosts, int64_t* rowIdx, int32_t* goodRows, int32_t device);
+int pda_to_probs_batch(double* values, const int64_t* off, const int64_t* len, int64_t nVectors, void* stream);
+int pda_to_probs_batch_host(double* values, const int64_t* off, const int64_t* len, int64_t nVectors, int32_t device);
+
+/* ------------------------------------------------------------------------------------------
+ * Matrix permanent, Nijenhuis-Wilf / Ryser over Gray-code column subsets.
+ * Replaces permanentExactSquare / permanentExact (nwPerm.h:22-24; nwPerm.cpp:217-231, 251-332).
+ *
+ * pda_permanent_batch: nMats matrices, matrix i is rows[i] x cols[i] at mats + matOff[i];
+ *   rectangular ones are padded with ones to max(rows, cols) and divided by (|rows-cols|)!
+ *   exactly as the reference does.  out[i] = permanent; status[i] = 0, or 1 where the
+ *   reference throws (dimension > 32).  maxDim >= max(rows[i], cols[i]) over the batch
+ *   (it selects the register tile; a batch is fastest when its matrices share one size).
+ * pda_permanent_range: partial NW sum of ONE n x n matrix over Gray indices [begin, end)
+ *   (index 0 = the empty-subset seed term), as an unevaluated double-double partial[0] + partial[1];
+ *   partial sums over disjoint ranges covering [0, 2^(n-1)) add up to p, and the permanent is
+ *   (4*(n&1)-2) * p.  This is the unit the multi-GPU split all-reduces.
+ * Results agree with the reference to ~1e-13 relative on well-conditioned inputs (the summation
+ * order differs: the walk is split into per-thread ranges and accumulated in double-double).
+ */
+int64_t pda_permanent_workspace_bytes(int64_t nMats);
+int pda_permanent_batch(const double* mats, const int64_t* matOff, const int32_t* rows, const int32_t* cols,
+                        int64_t nMats, int32_t maxDim, double* out, int32_t* status,
+                        void* workspace, int64_t workspaceBytes, void* stream);
+int pda_permanent_batch_host(const double* mats, const int64_t* matOff, const int32_t* rows, const int32_t* cols,
+                             int64_t nMats, double* out, int32_t* status, int32_t device);
+int pda_permanent_range(const double* A, int32_t n, uint64_t begin, uint64_t end, double* partial,
+                        void* workspace, int64_t workspaceBytes, void* stream);
+int pda_permanent_range_host(const double* A, int32_t n, uint64_t begin, uint64_t end, double* partial,
+                             int32_t device);
+
+/* conditionedPermanent (assignment.cpp:325-435) for a batch of matrices: zero rows/columns dropped,
+ * columns scaled, permanent of the transpose, negative-result retry.  permOpt 1 or 2. */
+int pda_conditioned_permanent_batch_host(const double* mats, const int64_t* matOff, const int32_t* rows,
+                                         const int32_t* cols, int64_t nMats, int32_t permOpt,
+                                         double* out, int32_t* status, int32_t device);
+
+/* permanentProb (assignment.cpp:145-290): permanent-based marginals for a batch of problems.
+ * probs at probOff[p], numCol[p] x (nL[p]+1) row-major; status[p] = 1 where the reference throws. */
+int pda_permanent_prob_batch_host(const double* costs, const int64_t* costOff, const int32_t* nL,
+                                  const int32_t* nM, int64_t nProblems, int32_t permOpt,
+                                  double* probs, const int64_t* probOff, int32_t* status, int32_t device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDA_B200_H */

@@ -1,0 +1,652 @@
+// murty_kernel.cu -- batched Murty k-best assignment enumeration for sm_100a.
+//
+// One warp owns one association problem at a time (persistent warps, atomic work
+// cursor).  The algorithm is the reference's (shortestPathCPP.cpp): a shortest-
+// augmenting-path LAP on the zero-padded square matrix for the root, then Murty's
+// partition where every child inherits the parent's duals and needs ONE Dijkstra
+// from the freed column (Miller-Stone-Cox).  What is different is where things live:
+//
+//   lane l owns rows  l, l+32, ...   (v, col4row, shortestPathCost, pred  in registers)
+//   lane l owns cols  l, l+32, ...   (u, row4col                            in registers)
+//   shared memory per warp: the shifted cost matrix (real columns only -- the
+//     reference's padding columns are exactly 0.0 and are never stored), a mirror of
+//     u / row4col for the data-dependent lookups, and the weight accumulators
+//   global memory per warp: a node arena (bump allocated, written once, read once)
+//     and the binary heap that orders the nodes
+//
+// The row scan of one Dijkstra step is a single pass over the lane's R rows; the
+// "closest row" is a warp arg-min done with three REDUX.MIN on an order-preserving
+// 64-bit key, lowest row index winning ties -- exactly the reference's first-minimum-
+// in-list-order rule because its Row2Scan lists are always ascending
+// (shortestPathCPP.cpp:155-157, 486, 215/345).  Every FP64 expression keeps the
+// reference's operand order (this file is compiled with -fmad=false; there is no
+// multiply on the path except CDelta*numCol), so row4col, col4row, gains and the
+// enumeration order are bit-identical to an IEEE-strict build of the reference.
+// The heap replays libstdc++'s __push_heap / __adjust_heap so that exact gain ties
+// pop in the same order as std::priority_queue<pMurtyHyp> (shortestPathCPP.cpp:30-42).
+#include "pda_internal.h"
+
+#include <math_constants.h>
+
+namespace pda {
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+struct __align__(16) HeapEntry {
+    double gain;
+    int node;
+    int pad;
+};
+
+// ---- order-preserving 64-bit key for doubles ----------------------------------------------------
+__device__ __forceinline__ void to_key(double d, unsigned& khi, unsigned& klo) {
+    const unsigned hi = (unsigned)__double2hiint(d), lo = (unsigned)__double2loint(d);
+    const unsigned m = (unsigned)((int)hi >> 31);  // all ones for negatives
+    khi = hi ^ (m | 0x80000000u);
+    klo = lo ^ m;
+}
+__device__ __forceinline__ double from_key(unsigned khi, unsigned klo) {
+    const unsigned m = (khi & 0x80000000u) ? 0u : 0xffffffffu;
+    return __hiloint2double((int)(khi ^ (m | 0x80000000u)), (int)(klo ^ m));
+}
+constexpr unsigned KEY_INF_HI = 0xFFF00000u;  // key of +inf is (0xFFF00000, 0)
+
+__device__ __forceinline__ double warp_min(double x) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { double y = __shfl_xor_sync(FULL, x, o); x = (y < x) ? y : x; }
+    return x;
+}
+__device__ __forceinline__ double warp_max(double x) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { double y = __shfl_xor_sync(FULL, x, o); x = (x < y) ? y : x; }
+    return x;
+}
+
+// Per-warp view of shared memory.
+struct WarpSmem {
+    double* C;       // [ld * numCol] shifted cost matrix, real columns only
+    double* u;       // [32R] mirror of the working node's column duals
+    double* spc;     // [32R] shortestPathCost, published after a scan for the dual update
+    double* acc;     // [numCol * (nL+1)] weight accumulators
+    short* r4c;      // [32R] mirror of the working node's row4col
+    short* pred;     // [32R] predecessor column per row
+};
+
+// The working node, distributed over the warp.
+template <int R>
+struct Node {
+    double v[R];   // row duals           (lane owns rows  lane + 32 s)
+    double u[R];   // column duals        (lane owns cols  lane + 32 s)
+    int c4r[R];    // column of each owned row (-1 = free)
+    int r4c[R];    // row of each owned column (-1 = free)
+};
+
+// One shortest augmenting path from `startCol` over the rows flagged in scanBits
+// (bit s = row lane+32s), then the dual update and the flip along the path.
+//   shortestPathCPP.cpp:168-226 / 297-356 (scan), :92-106 (duals), :108-116 (flip).
+// forbBits hides rows on the first hop only (:310).  numColReal = columns that exist in
+// sm.C; columns beyond are the reference's zero padding.  Returns true if infeasible.
+template <int R>
+__device__ __forceinline__ bool augment_from(const int startCol, const int numColReal, const int ld,
+                                             const WarpSmem& sm, Node<R>& nd, unsigned scanBits,
+                                             const unsigned forbBits, const int lane) {
+    double spc[R];
+    int pred[R];
+    unsigned colSeen[R];
+#pragma unroll
+    for (int s = 0; s < R; ++s) { spc[s] = CUDART_INF; pred[s] = 0; colSeen[s] = 0u; }
+    unsigned scannedBits = 0u;
+    unsigned hide = forbBits;  // cleared after the first hop
+    int cur = startCol, sink;
+    double delta = 0.0;
+
+    for (;;) {
+#pragma unroll
+        for (int s = 0; s < R; ++s)
+            if ((cur >> 5) == s) colSeen[s] |= 1u << (cur & 31);
+        const double ucur = sm.u[cur];
+        const bool real = cur < numColReal;
+        const double* Ccol = sm.C + cur * ld;
+        double best = CUDART_INF;
+        int bs = 0;
+        const unsigned act = scanBits & ~hide;
+#pragma unroll
+        for (int s = 0; s < R; ++s) {
+            if ((act >> s) & 1u) {
+                const double c = real ? Ccol[lane + 32 * s] : 0.0;
+                const double red = ((delta + c) - ucur) - nd.v[s];
+                if (red < spc[s]) { spc[s] = red; pred[s] = cur; }
+                if (spc[s] < best) { best = spc[s]; bs = s; }
+            }
+        }
+        hide = 0u;
+        best = best + 0.0;  // -0.0 and +0.0 compare equal in the reference; give them one key
+        unsigned khi, klo;
+        to_key(best, khi, klo);
+        const unsigned mhi = __reduce_min_sync(FULL, khi);
+        const unsigned mlo = __reduce_min_sync(FULL, (khi == mhi) ? klo : 0xffffffffu);
+        if (mhi == KEY_INF_HI && mlo == 0u) return true;  // minVal == +inf (:197, :327)
+        const bool win = (khi == mhi) && (klo == mlo);
+        const int closest = (int)__reduce_min_sync(FULL, win ? (unsigned)(lane + 32 * bs) : 0xffffu);
+        delta = from_key(mhi, mlo);
+
+        int mine = nd.c4r[0];
+#pragma unroll
+        for (int s = 0; s < R; ++s) {
+            if (lane + 32 * s == closest) { scanBits &= ~(1u << s); scannedBits |= 1u << s; }
+            if (s > 0 && (closest >> 5) == s) mine = nd.c4r[s];
+        }
+        const int next = __shfl_sync(FULL, mine, closest & 31);
+        if (next < 0) { sink = closest; break; }
+        cur = next;
+    }
+
+    // duals, using row4col as it was before the flip (:92-106)
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+        if ((scannedBits >> s) & 1u) nd.v[s] = (nd.v[s] - delta) + spc[s];
+        sm.spc[lane + 32 * s] = spc[s];
+        sm.pred[lane + 32 * s] = (short)pred[s];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+        if ((colSeen[s] >> lane) & 1u) {
+            const int c = lane + 32 * s;
+            if (c == startCol) nd.u[s] = nd.u[s] + delta;
+            else nd.u[s] = (nd.u[s] + delta) - sm.spc[nd.r4c[s]];
+            sm.u[c] = nd.u[s];
+        }
+    }
+    // flip along the predecessor chain (:108-116); sm.r4c still holds the pre-flip pairing
+    int r = sink, c;
+    do {
+        c = sm.pred[r];
+        const int h = sm.r4c[c];
+#pragma unroll
+        for (int s = 0; s < R; ++s) {
+            if (lane + 32 * s == r) nd.c4r[s] = c;
+            if (lane + 32 * s == c) nd.r4c[s] = r;
+        }
+        r = h;
+    } while (c != startCol);
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < R; ++s) sm.r4c[lane + 32 * s] = (short)nd.r4c[s];
+    __syncwarp();
+    return false;
+}
+
+// calcGain (:59-80): ascending column order, starting from 0.0.
+__device__ __forceinline__ double path_gain(const WarpSmem& sm, const int ld, const int numColGain) {
+    double g = 0.0;
+#pragma unroll 4
+    for (int c = 0; c < numColGain; ++c) g = g + sm.C[c * ld + sm.r4c[c]];
+    return g;
+}
+
+// ---- heap in the warp's arena: lane 0 only ---------------------------------------------------------
+__device__ __forceinline__ void heap_sift_up(HeapEntry* h, int hole, const HeapEntry val) {
+    int parent = (hole - 1) / 2;
+    while (hole > 0 && h[parent].gain > val.gain) {
+        h[hole] = h[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    h[hole] = val;
+}
+__device__ __forceinline__ void heap_pop(HeapEntry* h, const int lenBefore) {
+    if (lenBefore > 1) {
+        const int len = lenBefore - 1;
+        const HeapEntry val = h[len];
+        int hole = 0, child = 0;
+        while (child < (len - 1) / 2) {
+            child = 2 * (child + 1);
+            if (h[child].gain > h[child - 1].gain) child--;  // right child wins an exact tie
+            h[hole] = h[child];
+            hole = child;
+        }
+        if ((len & 1) == 0 && child == (len - 2) / 2) {
+            child = 2 * (child + 1);
+            h[hole] = h[child - 1];
+            hole = child - 1;
+        }
+        heap_sift_up(h, hole, val);
+    }
+}
+
+// ---- node arena -------------------------------------------------------------------------------------
+// layout of one stored node (D = geo.nodeDim):  v[D] | u[D] | c4r bytes[D] | r4c bytes[D] | forb words[R] | activeCol
+template <int R>
+__device__ __forceinline__ void node_store(unsigned char* base, const int D, const int n, const Node<R>& nd,
+                                           const unsigned forbBits, const int activeCol, const int lane) {
+    double* dv = reinterpret_cast<double*>(base);
+    unsigned char* bi = base + 16 * D;
+    unsigned* meta = reinterpret_cast<unsigned*>(base + 18 * D);
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+        const int i = lane + 32 * s;
+        if (i < n) {
+            dv[i] = nd.v[s];
+            dv[D + i] = nd.u[s];
+            bi[i] = (unsigned char)nd.c4r[s];
+            bi[D + i] = (unsigned char)nd.r4c[s];
+        }
+        const unsigned w = __ballot_sync(FULL, (forbBits >> s) & 1u);
+        if (lane == 0) meta[s] = w;
+    }
+    if (lane == 0) meta[R] = (unsigned)activeCol;
+}
+template <int R>
+__device__ __forceinline__ void node_load(const unsigned char* base, const int D, const int n, Node<R>& nd,
+                                          unsigned& forbBits, int& activeCol, const int lane) {
+    const double* dv = reinterpret_cast<const double*>(base);
+    const unsigned char* bi = base + 16 * D;
+    const unsigned* meta = reinterpret_cast<const unsigned*>(base + 18 * D);
+    forbBits = 0u;
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+        const int i = lane + 32 * s;
+        if (i < n) {
+            nd.v[s] = dv[i];
+            nd.u[s] = dv[D + i];
+            nd.c4r[s] = (int)(signed char)bi[i];
+            nd.r4c[s] = (int)(signed char)bi[D + i];
+        } else {
+            nd.v[s] = 0.0; nd.u[s] = 0.0; nd.c4r[s] = -1; nd.r4c[s] = -1;
+        }
+        forbBits |= ((meta[s] >> lane) & 1u) << s;
+    }
+    activeCol = (int)meta[R];
+}
+
+template <int R>
+__device__ __forceinline__ void publish_cols(const WarpSmem& sm, const Node<R>& nd, const int lane) {
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+        sm.u[lane + 32 * s] = nd.u[s];
+        sm.r4c[lane + 32 * s] = (short)nd.r4c[s];
+    }
+    __syncwarp();
+}
+
+// makeCostMatrixSafe (:534-569): shift so every entry is >= 0; returns the shift.
+__device__ __forceinline__ double stage_safe_matrix(const double* Cg, double* Cs, const int numEl,
+                                                    const bool maximize, const bool makeSafe, const int lane) {
+    if (!makeSafe) {
+        for (int i = lane; i < numEl; i += 32) Cs[i] = Cg[i];
+        __syncwarp();
+        return 0.0;
+    }
+    double d;
+    if (!maximize) {
+        d = CUDART_INF;
+        for (int i = lane; i < numEl; i += 32) { const double x = Cg[i]; d = (x < d) ? x : d; }
+        d = warp_min(d);
+        for (int i = lane; i < numEl; i += 32) Cs[i] = Cg[i] - d;
+    } else {
+        d = -CUDART_INF;
+        for (int i = lane; i < numEl; i += 32) { const double x = Cg[i]; d = (d < x) ? x : d; }
+        d = warp_max(d);
+        for (int i = lane; i < numEl; i += 32) Cs[i] = -Cg[i] + d;
+    }
+    __syncwarp();
+    return d;
+}
+
+template <int R>
+__device__ __forceinline__ void emit(const MurtyArgs& a, const long long p, const int slot, const int n, const int nc,
+                                     const Node<R>& nd, const double gainOut, const int lane) {
+    if (a.c4rBest) {
+        int64_t* o = a.c4rBest + a.c4rOff[p] + (int64_t)slot * n;
+#pragma unroll
+        for (int s = 0; s < R; ++s) if (lane + 32 * s < n) o[lane + 32 * s] = (int64_t)nd.c4r[s];
+    }
+    if (a.r4cBest) {
+        int64_t* o = a.r4cBest + a.r4cOff[p] + (int64_t)slot * nc;
+#pragma unroll
+        for (int s = 0; s < R; ++s) if (lane + 32 * s < nc) o[lane + 32 * s] = (int64_t)nd.r4c[s];
+    }
+    if (a.gainBest && lane == 0) a.gainBest[p * (long long)a.k + slot] = gainOut;
+}
+
+// assignmentProb / bruteForceProb accumulation of one hypothesis (assignment.cpp:620-640, 916-937)
+template <int R>
+__device__ __forceinline__ void add_weight(const MurtyArgs& a, const WarpSmem& sm, const Node<R>& nd, const int nc,
+                                           const int nL, const double best, const double gainOut, double& total,
+                                           const int lane) {
+    if (a.weightMode == PDA_WEIGHTS_GATED && !(best + a.weightGate > gainOut)) return;
+    const double w = exp(best - gainOut);
+    total += w;
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+        const int c = lane + 32 * s;
+        if (c < nc) {
+            const int to = nd.r4c[s] >= nL ? nL : nd.r4c[s];
+            sm.acc[c * (nL + 1) + to] += w;
+        }
+    }
+}
+
+template <int R>
+__device__ void solve_problem(const MurtyArgs& a, const long long p, const WarpSmem& sm, HeapEntry* heap,
+                              unsigned char* nodes, const int lane) {
+    const int n = a.numRow[p], nc = a.numCol[p];
+    const int D = a.geo.nodeDim;
+    const bool wantW = a.weightMode != PDA_WEIGHTS_NONE;
+    const int nL = wantW ? a.nL[p] : 0;
+    if (nc < 1 || nc > n || n > 32 * R || (wantW && nL + nc != n)) {
+        if (lane == 0) a.nFound[p] = 0;
+        return;
+    }
+    const double* Cg = a.costs + a.costOff[p];
+
+    // single-detection shortcut of assignmentProb / bruteForceProb (assignment.cpp:554-570, 840-856)
+    if (wantW && nc == 1) {
+        for (int i = lane; i <= nL; i += 32) sm.acc[i] = (Cg[i] < a.weightGate) ? exp(-Cg[i]) : 0.0;
+        __syncwarp();
+        double norm = 0.0;
+        for (int i = 0; i <= nL; ++i) if (Cg[i] < a.weightGate) norm += sm.acc[i];
+        norm = 1.0 / norm;
+        double* out = a.probs + a.probOff[p];
+        for (int i = lane; i <= nL; i += 32) out[i] = sm.acc[i] * norm;
+        __syncwarp();
+    }
+
+    const bool maximize = a.maximize != 0;
+    double CDelta = stage_safe_matrix(Cg, sm.C, n * nc, maximize, true, lane);
+    CDelta = CDelta * (double)nc;  // (:583, :664) a separately rounded product
+    if (wantW && nc > 1) {
+        for (int i = lane; i < nc * (nL + 1); i += 32) sm.acc[i] = 0.0;
+    }
+
+    // ---- root: shortestPathCPP on the zero-padded n x n matrix (:119-238) --------------------
+    Node<R> nd;
+#pragma unroll
+    for (int s = 0; s < R; ++s) { nd.v[s] = 0.0; nd.u[s] = 0.0; nd.c4r[s] = -1; nd.r4c[s] = -1; }
+    publish_cols<R>(sm, nd, lane);
+    unsigned allRows = 0u;
+#pragma unroll
+    for (int s = 0; s < R; ++s) if (lane + 32 * s < n) allRows |= 1u << s;
+    for (int c = 0; c < n; ++c) {
+        if (augment_from<R>(c, nc, n, sm, nd, allRows, 0u, lane)) {
+            if (lane == 0) a.nFound[p] = 0;
+            if (wantW && nc > 1) {  // the reference ends up scaling zeros by 1/0 here
+                double* out = a.probs + a.probOff[p];
+                for (int i = lane; i < nc * (nL + 1); i += 32) out[i] = CUDART_NAN;
+            }
+            return;
+        }
+    }
+    double gain = path_gain(sm, n, nc);
+    unsigned forb = 0u;
+    {
+        const int r0 = sm.r4c[0];
+#pragma unroll
+        for (int s = 0; s < R; ++s) if (lane + 32 * s == r0) forb |= 1u << s;
+    }
+    int activeCol = 0;
+
+    double gain0Out, cutoffGain = a.cutoff;
+    bool cutMax = a.cutMaximize != 0;
+    if (!maximize) {
+        if (a.cutMode == PDA_CUT_RELATIVE) { cutoffGain = gain + a.cutoff; cutMax = false; }
+        gain0Out = gain + CDelta;
+    } else {
+        if (a.cutMode == PDA_CUT_RELATIVE) { cutoffGain = gain - a.cutoff; cutMax = true; }
+        gain0Out = -gain + CDelta;
+    }
+    const bool cutting = a.cutMode != PDA_CUT_NONE;
+    emit<R>(a, p, 0, n, nc, nd, gain0Out, lane);
+    double total = 0.0;
+    if (wantW && nc > 1) add_weight<R>(a, sm, nd, nc, nL, gain0Out, gain0Out, total, lane);
+
+    int heapLen = 1;   // the root; its state is live in registers, slot 0 of the arena stays unused
+    int nNodes = 1;
+    int sweep = 1;
+    for (; sweep < a.k; ++sweep) {
+        // ---- pop the node whose state we hold (it is the heap top) ---------------------------
+        if (lane == 0) heap_pop(heap, heapLen);
+        heapLen--;
+        __syncwarp();
+
+        // ---- split (:455-532) --------------------------------------------------------------
+        Node<R> par = nd;
+        const unsigned parForb = forb;
+        const int a0 = activeCol;
+        unsigned inPar = 0u;  // Row2ScanParent: rows paired with columns >= a0
+#pragma unroll
+        for (int s = 0; s < R; ++s) if (lane + 32 * s < n && par.c4r[s] >= a0) inPar |= 1u << s;
+        for (int c = a0; c < nc; ++c) {
+            nd = par;
+            publish_cols<R>(sm, nd, lane);
+            const int r0 = sm.r4c[c];  // the pairing this child must give up
+            unsigned hideFirst = 0u;
+#pragma unroll
+            for (int s = 0; s < R; ++s) {
+                if (lane + 32 * s == r0) { nd.c4r[s] = -1; hideFirst |= 1u << s; }
+                if (lane + 32 * s == c) nd.r4c[s] = -1;
+            }
+            if (c == a0) hideFirst = parForb;  // first child inherits every constraint on the active column (:490)
+            const bool infeasible = augment_from<R>(c, nc, n, sm, nd, inPar, hideFirst, lane);
+            if (!infeasible) {
+                const double g = path_gain(sm, n, nc);
+                const bool cut = cutting && (cutMax ? (g < cutoffGain) : (g > cutoffGain));
+                if (!cut) {
+                    unsigned childForb = hideFirst;
+                    const int rNew = sm.r4c[c];
+#pragma unroll
+                    for (int s = 0; s < R; ++s) if (lane + 32 * s == rNew) childForb |= 1u << s;
+                    node_store<R>(nodes + (size_t)nNodes * a.geo.nodeStride, D, n, nd, childForb, c, lane);
+                    if (lane == 0) {
+                        HeapEntry e;
+                        e.gain = g; e.node = nNodes; e.pad = 0;
+                        heap_sift_up(heap, heapLen, e);
+                    }
+                    heapLen++;
+                    nNodes++;
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < R; ++s) if (lane + 32 * s == r0) inPar &= ~(1u << s);  // column c is fixed from here on
+        }
+        __syncwarp();
+        if (heapLen == 0) break;
+
+        // ---- the new top is hypothesis number `sweep` (:703-719) ---------------------------
+        HeapEntry top = heap[0];
+        gain = top.gain;
+        node_load<R>(nodes + (size_t)top.node * a.geo.nodeStride, D, n, nd, forb, activeCol, lane);
+        double gainOut;
+        bool stop = false;
+        if (!maximize) {
+            gainOut = gain + CDelta;
+            if (a.cutMode == PDA_CUT_RELATIVE && gainOut > gain0Out + a.cutoff) stop = true;
+        } else {
+            gainOut = -gain + CDelta;
+            if (a.cutMode == PDA_CUT_RELATIVE && gainOut < gain0Out - a.cutoff) stop = true;
+        }
+        emit<R>(a, p, sweep, n, nc, nd, gainOut, lane);
+        if (stop) break;
+        if (wantW && nc > 1) add_weight<R>(a, sm, nd, nc, nL, gain0Out, gainOut, total, lane);
+    }
+    if (lane == 0) a.nFound[p] = sweep;
+    if (wantW && nc > 1) {
+        __syncwarp();
+        const double norm = 1.0 / total;
+        double* out = a.probs + a.probOff[p];
+        for (int i = lane; i < nc * (nL + 1); i += 32) out[i] = sm.acc[i] * norm;
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ WarpSmem carve(unsigned char* base, const MurtyGeometry& g) {
+    WarpSmem sm;
+    const int D = 32 * g.R;
+    sm.C = reinterpret_cast<double*>(base);
+    sm.u = sm.C + g.cCap;
+    sm.spc = sm.u + D;
+    sm.acc = sm.spc + D;
+    sm.r4c = reinterpret_cast<short*>(sm.acc + g.pCap);
+    sm.pred = sm.r4c + D;
+    return sm;
+}
+
+template <int R>
+__global__ void murty_kernel(const MurtyArgs a) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gw = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (gw >= a.nWarps) return;
+    const WarpSmem sm = carve(smemRaw + (size_t)warp * a.geo.smemPerWarp, a.geo);
+    unsigned char* arena = a.arena + (size_t)gw * a.geo.arenaStride;
+    HeapEntry* heap = reinterpret_cast<HeapEntry*>(arena);
+    unsigned char* nodes = arena + a.geo.heapBytes;
+    for (;;) {
+        unsigned long long p = 0;
+        if (lane == 0) p = atomicAdd(a.cursor, 1ULL);
+        p = __shfl_sync(FULL, p, 0);
+        if ((long long)p >= a.nProblems) break;
+        solve_problem<R>(a, (long long)p, sm, heap, nodes, lane);
+        __syncwarp();
+    }
+}
+
+// ---- plain LAP (assign2D / shortestPathCPP on a rectangular matrix, no padding) ---------------------
+template <int R>
+__global__ void lap_kernel(const LapArgs a, const int smemPerWarp, const int cCap) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long p = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (p >= a.nProblems) return;
+    MurtyGeometry g;
+    g.R = R; g.cCap = cCap; g.pCap = 0;
+    const WarpSmem sm = carve(smemRaw + (size_t)warp * smemPerWarp, g);
+    const int n = a.numRow[p], nc = a.numCol[p];
+    const int ncGain = a.numCol4Gain ? a.numCol4Gain[p] : nc;
+    if (nc < 0 || nc > n || n > 32 * R) { if (lane == 0 && a.feasible) a.feasible[p] = 0; return; }
+    double CDelta = stage_safe_matrix(a.costs + a.costOff[p], sm.C, n * nc, a.maximize != 0, a.makeSafe != 0, lane);
+    CDelta = CDelta * (double)nc;
+    Node<R> nd;
+#pragma unroll
+    for (int s = 0; s < R; ++s) { nd.v[s] = 0.0; nd.u[s] = 0.0; nd.c4r[s] = -1; nd.r4c[s] = -1; }
+    publish_cols<R>(sm, nd, lane);
+    unsigned allRows = 0u;
+#pragma unroll
+    for (int s = 0; s < R; ++s) if (lane + 32 * s < n) allRows |= 1u << s;
+    bool infeasible = false;
+    for (int c = 0; c < nc && !infeasible; ++c) infeasible = augment_from<R>(c, nc, n, sm, nd, allRows, 0u, lane);
+    double gain = -1.0;
+    int r0 = -1;
+    if (!infeasible) {
+        gain = path_gain(sm, n, ncGain);
+        if (a.makeSafe) gain = a.maximize ? (-gain + CDelta) : (gain + CDelta);
+        if (nc > 0) r0 = sm.r4c[0];
+    }
+    const int64_t ro = a.rowOff[p], co = a.colOff[p];
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+        const int i = lane + 32 * s;
+        if (i < n) {
+            if (a.col4row) a.col4row[ro + i] = nd.c4r[s];
+            if (a.v) a.v[ro + i] = nd.v[s];
+            if (a.forbidden) a.forbidden[ro + i] = (i == r0) ? 1 : 0;
+        }
+        if (i < nc) {
+            if (a.row4col) a.row4col[co + i] = nd.r4c[s];
+            if (a.u) a.u[co + i] = nd.u[s];
+        }
+    }
+    if (lane == 0) {
+        if (a.gain) a.gain[p] = gain;
+        if (a.feasible) a.feasible[p] = infeasible ? 0 : 1;
+    }
+}
+
+}  // namespace
+
+// ---- host side ------------------------------------------------------------------------------------
+static int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+int murty_geometry(int32_t k, int32_t maxNumRow, int32_t maxNumCol, bool weights, const DeviceInfo& dev,
+                   MurtyGeometry* g) {
+    if (k < 1 || maxNumRow < 1 || maxNumCol < 1 || maxNumCol > maxNumRow)
+        return fail(PDA_ERR_INVALID, "murty: need k >= 1 and 1 <= maxNumCol <= maxNumRow (got k=%d, %d x %d)", k, maxNumRow, maxNumCol);
+    if (maxNumRow > PDA_MAX_DIM)
+        return fail(PDA_ERR_UNSUPPORTED, "murty: numRow %d exceeds PDA_MAX_DIM %d", maxNumRow, PDA_MAX_DIM);
+    g->R = (maxNumRow + 31) / 32;
+    if (g->R == 3) g->R = 4;
+    const int D = 32 * g->R;
+    g->nodeDim = round_up(maxNumRow, 8);
+    g->nodeStride = round_up(18 * g->nodeDim + 4 * (g->R + 1), 16);
+    const int64_t nodes = 1 + (int64_t)(k - 1) * maxNumCol;  // every pop creates at most numCol children
+    if (nodes > (int64_t)1 << 30) return fail(PDA_ERR_UNSUPPORTED, "murty: k * numCol too large");
+    g->maxNodes = (int)nodes;
+    g->heapBytes = (int64_t)round_up((int)nodes, 8) * (int64_t)sizeof(HeapEntry);
+    g->arenaStride = (g->heapBytes + nodes * g->nodeStride + 255) / 256 * 256;
+    g->cCap = round_up(maxNumRow * maxNumCol, 2);
+    g->pCap = weights ? round_up(maxNumCol * maxNumRow, 2) : 0;
+    g->smemPerWarp = round_up(8 * (g->cCap + g->pCap + 2 * D) + 2 * 2 * D, 16);
+    if (g->smemPerWarp > dev.maxSmemOptin)
+        return fail(PDA_ERR_UNSUPPORTED, "murty: a %d x %d problem needs %d B of shared memory per warp (limit %d)",
+                    maxNumRow, maxNumCol, g->smemPerWarp, dev.maxSmemOptin);
+    int wpc = 4;
+    while (wpc > 1 && wpc * g->smemPerWarp > dev.maxSmemOptin) wpc >>= 1;
+    g->warpsPerCta = wpc;
+    // resident CTAs per SM: bounded by shared memory (227 KB usable, ~1 KB reserved per CTA) and by 32 warps/SM
+    int byS = (227 * 1024) / (wpc * g->smemPerWarp + 1024);
+    int byW = 32 / wpc;
+    g->ctasPerSm = byS < 1 ? 1 : (byS < byW ? byS : byW);
+    return PDA_OK;
+}
+
+template <int R>
+static int launch_murty_r(const MurtyArgs& a, cudaStream_t stream) {
+    const int threads = 32 * a.geo.warpsPerCta;
+    const int smem = a.geo.warpsPerCta * a.geo.smemPerWarp;
+    PDA_CUDA_TRY(cudaFuncSetAttribute(murty_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int ctas = (a.nWarps + a.geo.warpsPerCta - 1) / a.geo.warpsPerCta;
+    murty_kernel<R><<<ctas, threads, smem, stream>>>(a);
+    PDA_CUDA_TRY(cudaGetLastError());
+    return PDA_OK;
+}
+
+int launch_murty(const MurtyArgs& a, cudaStream_t stream) {
+    PDA_CUDA_TRY(cudaMemsetAsync(a.cursor, 0, sizeof(unsigned long long), stream));
+    switch (a.geo.R) {
+        case 1: return launch_murty_r<1>(a, stream);
+        case 2: return launch_murty_r<2>(a, stream);
+        case 4: return launch_murty_r<4>(a, stream);
+    }
+    return fail(PDA_ERR_UNSUPPORTED, "murty: unsupported row-slot count %d", a.geo.R);
+}
+
+template <int R>
+static int launch_lap_r(const LapArgs& a, cudaStream_t stream, const DeviceInfo& dev) {
+    const int D = 32 * R;
+    const int cCap = round_up(a.maxNumRow * a.maxNumCol, 2);
+    const int smemPerWarp = round_up(8 * (cCap + 2 * D) + 4 * D, 16);
+    if (smemPerWarp > dev.maxSmemOptin) return fail(PDA_ERR_UNSUPPORTED, "lap: matrix too large for shared memory");
+    int wpc = 4;
+    while (wpc > 1 && wpc * smemPerWarp > dev.maxSmemOptin) wpc >>= 1;
+    const int smem = wpc * smemPerWarp;
+    PDA_CUDA_TRY(cudaFuncSetAttribute(lap_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const long long ctas = (a.nProblems + wpc - 1) / wpc;
+    lap_kernel<R><<<(unsigned)ctas, 32 * wpc, smem, stream>>>(a, smemPerWarp, cCap);
+    PDA_CUDA_TRY(cudaGetLastError());
+    return PDA_OK;
+}
+
+int launch_lap(const LapArgs& a, cudaStream_t stream) {
+    DeviceInfo dev;
+    int rc = current_device_info(&dev);
+    if (rc) return rc;
+    if (a.maxNumRow > PDA_MAX_DIM) return fail(PDA_ERR_UNSUPPORTED, "lap: numRow %d exceeds PDA_MAX_DIM", a.maxNumRow);
+    const int R = (a.maxNumRow + 31) / 32;
+    if (R <= 1) return launch_lap_r<1>(a, stream, dev);
+    if (R == 2) return launch_lap_r<2>(a, stream, dev);
+    return launch_lap_r<4>(a, stream, dev);
+}
+
+}  // namespace pda

@@ -1,0 +1,252 @@
+// pda_capi.cu -- the extern "C" surface of libpda_b200.so (include/pda_b200.h):
+// argument checking, workspace geometry, kernel launches, and the *_host convenience
+// entry points that stage host buffers through a cached, grow-only device arena.
+// There is deliberately no CPU path in here: without a CUDA device every compute
+// call fails with PDA_ERR_CUDA.
+#include "pda_internal.h"
+#include "pda_host_stage.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+namespace pda {
+
+static thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    (void)cudaGetLastError();
+    return PDA_ERR_CUDA;
+}
+
+int current_device_info(DeviceInfo* out) {
+    int dev = 0;
+    PDA_CUDA_TRY(cudaGetDevice(&dev));
+    static std::mutex mu;
+    static std::vector<DeviceInfo> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    for (const DeviceInfo& d : cache)
+        if (d.device == dev) { *out = d; return PDA_OK; }
+    DeviceInfo d;
+    d.device = dev;
+    PDA_CUDA_TRY(cudaDeviceGetAttribute(&d.smCount, cudaDevAttrMultiProcessorCount, dev));
+    PDA_CUDA_TRY(cudaDeviceGetAttribute(&d.maxSmemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    cache.push_back(d);
+    *out = d;
+    return PDA_OK;
+}
+
+std::mutex g_hostMu;
+std::vector<DevArena> g_arenas;
+
+}  // namespace pda
+
+using namespace pda;
+
+extern "C" {
+
+int pda_version(void) { return 100; }
+const char* pda_last_error(void) { return g_err; }
+int pda_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------- Murty
+static int64_t murty_full_warps(const MurtyGeometry& g, const DeviceInfo& dev) {
+    return (int64_t)dev.smCount * g.ctasPerSm * g.warpsPerCta;
+}
+
+int64_t pda_murty_workspace_bytes(int64_t nProblems, int32_t k, int32_t maxNumRow, int32_t maxNumCol) {
+    DeviceInfo dev;
+    int rc = current_device_info(&dev);
+    if (rc) return rc;
+    MurtyGeometry g;
+    rc = murty_geometry(k, maxNumRow, maxNumCol, false, dev, &g);
+    if (rc) return rc;
+    int64_t warps = std::min<int64_t>(std::max<int64_t>(nProblems, 1), murty_full_warps(g, dev));
+    return 256 + warps * g.arenaStride;
+}
+
+int pda_murty_batch(const double* costs, const int64_t* costOff, const int32_t* numRow, const int32_t* numCol,
+                    int64_t nProblems, int32_t maxNumRow, int32_t maxNumCol,
+                    int32_t k, int32_t cutMode, double cutoff, int32_t maximize, int32_t cutMaximize,
+                    int64_t* row4colBest, const int64_t* r4cOff,
+                    int64_t* col4rowBest, const int64_t* c4rOff,
+                    double* gainBest, int32_t* nFound,
+                    int32_t weightMode, double* probs, const int64_t* probOff, const int32_t* nL,
+                    void* workspace, int64_t workspaceBytes, void* stream) {
+    if (nProblems < 0) return fail(PDA_ERR_INVALID, "murty: nProblems < 0");
+    if (nProblems == 0) return PDA_OK;
+    if (!costs || !costOff || !numRow || !numCol || !nFound) return fail(PDA_ERR_INVALID, "murty: NULL input");
+    if ((row4colBest && !r4cOff) || (col4rowBest && !c4rOff)) return fail(PDA_ERR_INVALID, "murty: output given without offsets");
+    if (cutMode < PDA_CUT_NONE || cutMode > PDA_CUT_STICKY) return fail(PDA_ERR_INVALID, "murty: bad cutMode %d", cutMode);
+    if (weightMode < PDA_WEIGHTS_NONE || weightMode > PDA_WEIGHTS_UNGATED) return fail(PDA_ERR_INVALID, "murty: bad weightMode %d", weightMode);
+    if (weightMode && (!probs || !probOff || !nL)) return fail(PDA_ERR_INVALID, "murty: weights requested without probs/probOff/nL");
+    if (!workspace) return fail(PDA_ERR_WORKSPACE, "murty: NULL workspace");
+    DeviceInfo dev;
+    PDA_TRY(current_device_info(&dev));
+    MurtyArgs a;
+    PDA_TRY(murty_geometry(k, maxNumRow, maxNumCol, weightMode != 0, dev, &a.geo));
+    int64_t warps = std::min<int64_t>(nProblems, murty_full_warps(a.geo, dev));
+    warps = std::min<int64_t>(warps, (workspaceBytes - 256) / a.geo.arenaStride);
+    if (warps < 1) return fail(PDA_ERR_WORKSPACE, "murty: workspace of %lld B holds no arena (%lld B each)",
+                               (long long)workspaceBytes, (long long)a.geo.arenaStride);
+    a.costs = costs; a.costOff = costOff; a.numRow = numRow; a.numCol = numCol; a.nProblems = nProblems;
+    a.k = k; a.cutMode = cutMode; a.maximize = maximize; a.cutMaximize = cutMaximize; a.cutoff = cutoff;
+    a.r4cBest = row4colBest; a.r4cOff = r4cOff; a.c4rBest = col4rowBest; a.c4rOff = c4rOff;
+    a.gainBest = gainBest; a.nFound = nFound;
+    a.weightMode = weightMode; a.weightGate = 42.0;  // assignment.cpp:9
+    a.probs = probs; a.probOff = probOff; a.nL = nL;
+    a.cursor = reinterpret_cast<unsigned long long*>(workspace);
+    a.arena = reinterpret_cast<unsigned char*>(workspace) + 256;
+    a.nWarps = (int32_t)warps;
+    return launch_murty(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int pda_murty_batch_host(const double* costs, const int64_t* costOff, const int32_t* numRow, const int32_t* numCol,
+                         int64_t nProblems, int32_t k, int32_t cutMode, double cutoff, int32_t maximize,
+                         int32_t cutMaximize,
+                         int64_t* row4colBest, const int64_t* r4cOff,
+                         int64_t* col4rowBest, const int64_t* c4rOff,
+                         double* gainBest, int32_t* nFound,
+                         int32_t weightMode, double* probs, const int64_t* probOff, const int32_t* nL,
+                         int32_t device) {
+    if (nProblems < 0) return fail(PDA_ERR_INVALID, "murty: nProblems < 0");
+    if (nProblems == 0) return PDA_OK;
+    if (!costs || !costOff || !numRow || !numCol || !nFound) return fail(PDA_ERR_INVALID, "murty: NULL input");
+    if (k < 1) return fail(PDA_ERR_INVALID, "murty: k < 1");
+    if (weightMode && (!probs || !probOff || !nL)) return fail(PDA_ERR_INVALID, "murty: weights requested without probs/probOff/nL");
+    int maxR = 0, maxC = 0;
+    size_t nCost = 0, nR4c = 0, nC4r = 0, nProb = 0;
+    for (int64_t p = 0; p < nProblems; ++p) {
+        const int r = numRow[p], c = numCol[p];
+        if (r < 1 || c < 1 || c > r) return fail(PDA_ERR_INVALID, "murty: problem %lld is %d x %d (need numRow >= numCol >= 1)", (long long)p, r, c);
+        maxR = std::max(maxR, r); maxC = std::max(maxC, c);
+        nCost = std::max(nCost, (size_t)costOff[p] + (size_t)r * c);
+        if (row4colBest) nR4c = std::max(nR4c, (size_t)r4cOff[p] + (size_t)k * c);
+        if (col4rowBest) nC4r = std::max(nC4r, (size_t)c4rOff[p] + (size_t)k * r);
+        if (weightMode) {
+            if (nL[p] + c != r) return fail(PDA_ERR_INVALID, "murty: problem %lld has nL + numCol != numRow", (long long)p);
+            nProb = std::max(nProb, (size_t)probOff[p] + (size_t)c * (nL[p] + 1));
+        }
+    }
+    std::lock_guard<std::mutex> lk(g_hostMu);
+    PDA_TRY(check_device(device));
+    int64_t wsBytes = pda_murty_workspace_bytes(nProblems, k, maxR, maxC);
+    if (wsBytes < 0) return (int)wsBytes;
+    const size_t n = (size_t)nProblems;
+    Stage st(device);
+    const size_t oCost = st.reserve(nCost * 8), oCostOff = st.reserve(n * 8), oNR = st.reserve(n * 4), oNC = st.reserve(n * 4);
+    const size_t oR4c = st.reserve(nR4c * 8), oR4cOff = st.reserve(n * 8), oC4r = st.reserve(nC4r * 8), oC4rOff = st.reserve(n * 8);
+    const size_t oGain = st.reserve(gainBest ? n * k * 8 : 0), oFound = st.reserve(n * 4);
+    const size_t oProb = st.reserve(nProb * 8), oProbOff = st.reserve(n * 8), oNL = st.reserve(n * 4);
+    const size_t oWs = st.reserve((size_t)wsBytes);
+    PDA_TRY(st.commit());
+    cudaStream_t s = 0;
+    PDA_TRY(h2d(st.at<double>(oCost), costs, nCost, s));
+    PDA_TRY(h2d(st.at<int64_t>(oCostOff), costOff, n, s));
+    PDA_TRY(h2d(st.at<int32_t>(oNR), numRow, n, s));
+    PDA_TRY(h2d(st.at<int32_t>(oNC), numCol, n, s));
+    if (row4colBest) PDA_TRY(h2d(st.at<int64_t>(oR4cOff), r4cOff, n, s));
+    if (col4rowBest) PDA_TRY(h2d(st.at<int64_t>(oC4rOff), c4rOff, n, s));
+    if (weightMode) {
+        PDA_TRY(h2d(st.at<int64_t>(oProbOff), probOff, n, s));
+        PDA_TRY(h2d(st.at<int32_t>(oNL), nL, n, s));
+    }
+    PDA_TRY(pda_murty_batch(st.at<double>(oCost), st.at<int64_t>(oCostOff), st.at<int32_t>(oNR), st.at<int32_t>(oNC),
+                            nProblems, maxR, maxC, k, cutMode, cutoff, maximize, cutMaximize,
+                            row4colBest ? st.at<int64_t>(oR4c) : nullptr, st.at<int64_t>(oR4cOff),
+                            col4rowBest ? st.at<int64_t>(oC4r) : nullptr, st.at<int64_t>(oC4rOff),
+                            gainBest ? st.at<double>(oGain) : nullptr, st.at<int32_t>(oFound),
+                            weightMode, weightMode ? st.at<double>(oProb) : nullptr, st.at<int64_t>(oProbOff),
+                            st.at<int32_t>(oNL), st.at<unsigned char>(oWs), wsBytes, s));
+    PDA_TRY(d2h(row4colBest, st.at<int64_t>(oR4c), nR4c, s));
+    PDA_TRY(d2h(col4rowBest, st.at<int64_t>(oC4r), nC4r, s));
+    PDA_TRY(d2h(gainBest, st.at<double>(oGain), n * k, s));
+    PDA_TRY(d2h(nFound, st.at<int32_t>(oFound), n, s));
+    if (weightMode) PDA_TRY(d2h(probs, st.at<double>(oProb), nProb, s));
+    PDA_CUDA_TRY(cudaStreamSynchronize(s));
+    return PDA_OK;
+}
+
+// ------------------------------------------------------------------------------------------- LAP
+int pda_lap_batch(const double* costs, const int64_t* costOff, const int32_t* numRow, const int32_t* numCol,
+                  const int32_t* numCol4Gain, int64_t nProblems, int32_t maxNumRow, int32_t maxNumCol,
+                  int32_t makeSafe, int32_t maximize,
+                  const int64_t* rowOff, const int64_t* colOff,
+                  int64_t* col4row, int64_t* row4col, double* u, double* v, uint8_t* forbidden,
+                  double* gain, int32_t* feasible, void* stream) {
+    if (nProblems < 0) return fail(PDA_ERR_INVALID, "lap: nProblems < 0");
+    if (nProblems == 0) return PDA_OK;
+    if (!costs || !costOff || !numRow || !numCol || !rowOff || !colOff) return fail(PDA_ERR_INVALID, "lap: NULL input");
+    if (maxNumRow < 1 || maxNumCol < 0 || maxNumCol > maxNumRow) return fail(PDA_ERR_INVALID, "lap: bad maximal dimensions");
+    LapArgs a = {costs, costOff, numRow, numCol, numCol4Gain, nProblems, makeSafe, maximize, rowOff, colOff,
+                 col4row, row4col, u, v, forbidden, gain, feasible, maxNumRow, std::max(maxNumCol, 1)};
+    return launch_lap(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int pda_lap_batch_host(const double* costs, const int64_t* costOff, const int32_t* numRow, const int32_t* numCol,
+                       const int32_t* numCol4Gain, int64_t nProblems, int32_t makeSafe, int32_t maximize,
+                       const int64_t* rowOff, const int64_t* colOff,
+                       int64_t* col4row, int64_t* row4col, double* u, double* v, uint8_t* forbidden,
+                       double* gain, int32_t* feasible, int32_t device) {
+    if (nProblems < 0) return fail(PDA_ERR_INVALID, "lap: nProblems < 0");
+    if (nProblems == 0) return PDA_OK;
+    if (!costs || !costOff || !numRow || !numCol || !rowOff || !colOff) return fail(PDA_ERR_INVALID, "lap: NULL input");
+    int maxR = 0, maxC = 0;
+    size_t nCost = 0, nRows = 0, nCols = 0;
+    for (int64_t p = 0; p < nProblems; ++p) {
+        const int r = numRow[p], c = numCol[p];
+        if (r < 1 || c < 0 || c > r) return fail(PDA_ERR_INVALID, "lap: problem %lld is %d x %d", (long long)p, r, c);
+        maxR = std::max(maxR, r); maxC = std::max(maxC, c);
+        nCost = std::max(nCost, (size_t)costOff[p] + (size_t)r * c);
+        nRows = std::max(nRows, (size_t)rowOff[p] + r);
+        nCols = std::max(nCols, (size_t)colOff[p] + c);
+    }
+    std::lock_guard<std::mutex> lk(g_hostMu);
+    PDA_TRY(check_device(device));
+    const size_t n = (size_t)nProblems;
+    Stage st(device);
+    const size_t oCost = st.reserve(nCost * 8), oCostOff = st.reserve(n * 8), oNR = st.reserve(n * 4), oNC = st.reserve(n * 4);
+    const size_t oNG = st.reserve(n * 4), oRO = st.reserve(n * 8), oCO = st.reserve(n * 8);
+    const size_t oC4r = st.reserve(nRows * 8), oR4c = st.reserve(nCols * 8), oU = st.reserve(nCols * 8), oV = st.reserve(nRows * 8);
+    const size_t oF = st.reserve(nRows), oG = st.reserve(n * 8), oFe = st.reserve(n * 4);
+    PDA_TRY(st.commit());
+    cudaStream_t s = 0;
+    PDA_TRY(h2d(st.at<double>(oCost), costs, nCost, s));
+    PDA_TRY(h2d(st.at<int64_t>(oCostOff), costOff, n, s));
+    PDA_TRY(h2d(st.at<int32_t>(oNR), numRow, n, s));
+    PDA_TRY(h2d(st.at<int32_t>(oNC), numCol, n, s));
+    if (numCol4Gain) PDA_TRY(h2d(st.at<int32_t>(oNG), numCol4Gain, n, s));
+    PDA_TRY(h2d(st.at<int64_t>(oRO), rowOff, n, s));
+    PDA_TRY(h2d(st.at<int64_t>(oCO), colOff, n, s));
+    PDA_TRY(pda_lap_batch(st.at<double>(oCost), st.at<int64_t>(oCostOff), st.at<int32_t>(oNR), st.at<int32_t>(oNC),
+                          numCol4Gain ? st.at<int32_t>(oNG) : nullptr, nProblems, maxR, maxC, makeSafe, maximize,
+                          st.at<int64_t>(oRO), st.at<int64_t>(oCO), st.at<int64_t>(oC4r), st.at<int64_t>(oR4c),
+                          st.at<double>(oU), st.at<double>(oV), st.at<uint8_t>(oF), st.at<double>(oG),
+                          st.at<int32_t>(oFe), s));
+    PDA_TRY(d2h(col4row, st.at<int64_t>(oC4r), nRows, s));
+    PDA_TRY(d2h(row4col, st.at<int64_t>(oR4c), nCols, s));
+    PDA_TRY(d2h(u, st.at<double>(oU), nCols, s));
+    PDA_TRY(d2h(v, st.at<double>(oV), nRows, s));
+    PDA_TRY(d2h(forbidden, st.at<uint8_t>(oF), nRows, s));
+    PDA_TRY(d2h(gain, st.at<double>(oG), n, s));
+    PDA_TRY(d2h(feasible, st.at<int32_t>(oFe), n, s));
+    PDA_CUDA_TRY(cudaStreamSynchronize(s));
+    return PDA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,73 @@
+// pda_host_stage.h -- helpers for the *_host entry points: a grow-only device arena per
+// device (so a batch-of-one shim call does not pay cudaMalloc/cudaFree every time) and
+// checked async copies.  One *_host call at a time (g_hostMu).
+#ifndef PDA_HOST_STAGE_H
+#define PDA_HOST_STAGE_H
+
+#include "pda_internal.h"
+
+#include <mutex>
+#include <vector>
+
+namespace pda {
+
+extern std::mutex g_hostMu;
+struct DevArena { int device; unsigned char* base; size_t cap; };
+extern std::vector<DevArena> g_arenas;
+
+class Stage {
+public:
+    explicit Stage(int device) : device_(device), used_(0), base_(nullptr) {}
+    // first pass: reserve() everything; then commit(); then at<T>(offset)
+    size_t reserve(size_t bytes) { size_t o = used_; used_ += (bytes + 255) / 256 * 256; return o; }
+    int commit() {
+        for (DevArena& a : g_arenas)
+            if (a.device == device_) {
+                if (a.cap < used_) {
+                    if (a.base) cudaFree(a.base);
+                    a.base = nullptr; a.cap = 0;
+                    size_t want = used_ + used_ / 4;
+                    cudaError_t e = cudaMalloc(&a.base, want);
+                    if (e != cudaSuccess) { (void)cudaGetLastError(); want = used_; e = cudaMalloc(&a.base, want); }
+                    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(host staging arena)");
+                    a.cap = want;
+                }
+                base_ = a.base;
+                return PDA_OK;
+            }
+        DevArena a = {device_, nullptr, 0};
+        g_arenas.push_back(a);
+        return commit();
+    }
+    template <class T> T* at(size_t off) const { return reinterpret_cast<T*>(base_ + off); }
+    size_t used() const { return used_; }
+private:
+    int device_; size_t used_; unsigned char* base_;
+};
+
+inline int check_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        (void)cudaGetLastError();
+        return fail(PDA_ERR_CUDA, "no CUDA device available (libpda_b200 has no CPU fallback)");
+    }
+    if (device < 0 || device >= n) return fail(PDA_ERR_INVALID, "device %d out of range (have %d)", device, n);
+    PDA_CUDA_TRY(cudaSetDevice(device));
+    return PDA_OK;
+}
+
+template <class T> inline int h2d(T* dst, const T* src, size_t n, cudaStream_t s) {
+    if (n == 0) return PDA_OK;
+    PDA_CUDA_TRY(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, s));
+    return PDA_OK;
+}
+template <class T> inline int d2h(T* dst, const T* src, size_t n, cudaStream_t s) {
+    if (n == 0 || dst == nullptr) return PDA_OK;
+    PDA_CUDA_TRY(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, s));
+    return PDA_OK;
+}
+#define PDA_TRY(expr) do { int _rc = (expr); if (_rc != PDA_OK) return _rc; } while (0)
+
+}  // namespace pda
+#endif

@@ -1,0 +1,88 @@
+// pda_internal.h -- declarations shared by the .cu files of libpda_b200.so.
+#ifndef PDA_INTERNAL_H
+#define PDA_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pda_b200.h"
+
+namespace pda {
+
+// ---- error plumbing (pda_capi.cu) -------------------------------------------------------
+int fail(int code, const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+#define PDA_CUDA_TRY(expr)                                           \
+    do {                                                             \
+        cudaError_t _e = (expr);                                     \
+        if (_e != cudaSuccess) return ::pda::cuda_fail(_e, #expr);   \
+    } while (0)
+
+struct DeviceInfo {
+    int device;
+    int smCount;
+    int maxSmemOptin;  // bytes per block, opt-in
+};
+int current_device_info(DeviceInfo* out);
+
+// ---- Murty k-best (murty_kernel.cu) ----------------------------------------------------------
+struct MurtyGeometry {
+    int R;              // row slots per lane: numRow <= 32*R
+    int nodeDim;        // padded per-node array length
+    int nodeStride;     // bytes per stored node
+    int maxNodes;       // node slots per warp arena
+    int64_t heapBytes;  // bytes of the heap region at the head of each arena
+    int64_t arenaStride;
+    int smemPerWarp;
+    int cCap;           // doubles reserved for the cost matrix per warp
+    int pCap;           // doubles reserved for the weight accumulators per warp
+    int warpsPerCta;
+    int ctasPerSm;
+};
+int murty_geometry(int32_t k, int32_t maxNumRow, int32_t maxNumCol, bool weights, const DeviceInfo& dev,
+                   MurtyGeometry* g);
+
+struct MurtyArgs {
+    const double* costs; const int64_t* costOff; const int32_t* numRow; const int32_t* numCol;
+    int64_t nProblems;
+    int32_t k, cutMode, maximize, cutMaximize;
+    double cutoff;
+    int64_t* r4cBest; const int64_t* r4cOff;
+    int64_t* c4rBest; const int64_t* c4rOff;
+    double* gainBest; int32_t* nFound;
+    int32_t weightMode; double weightGate;
+    double* probs; const int64_t* probOff; const int32_t* nL;
+    unsigned char* arena;
+    unsigned long long* cursor;  // work-queue cursor (zeroed before launch)
+    int32_t nWarps;              // arenas available == warps allowed to run
+    MurtyGeometry geo;
+};
+int launch_murty(const MurtyArgs& a, cudaStream_t stream);
+
+struct LapArgs {
+    const double* costs; const int64_t* costOff; const int32_t* numRow; const int32_t* numCol;
+    const int32_t* numCol4Gain;
+    int64_t nProblems;
+    int32_t makeSafe, maximize;
+    const int64_t* rowOff; const int64_t* colOff;
+    int64_t* col4row; int64_t* row4col; double* u; double* v; uint8_t* forbidden;
+    double* gain; int32_t* feasible;
+    int32_t maxNumRow, maxNumCol;
+};
+int launch_lap(const LapArgs& a, cudaStream_t stream);
+
+// ---- conditioning / likelihoods (weights_kernel.cu) --------------------------------------------
+int launch_condition_costs(const double* costs, const int64_t* costOff, const int32_t* numRow,
+                           const int32_t* numCol, int64_t nProblems, const int64_t* rowOff,
+                           double* outCosts, int64_t* rowIdx, int32_t* goodRows, cudaStream_t stream);
+int launch_to_probs(double* values, const int64_t* off, const int64_t* len, int64_t nVectors, cudaStream_t stream);
+
+// ---- permanents (permanent_kernel.cu) ------------------------------------------------------------
+int launch_permanent_batch(const double* mats, const int64_t* matOff, const int32_t* rows, const int32_t* cols,
+                           int64_t nMats, int32_t maxDim, double* out, int32_t* status, void* workspace,
+                           int64_t workspaceBytes, cudaStream_t stream);
+int launch_permanent_range(const double* A, int32_t n, uint64_t begin, uint64_t end, double* partial,
+                           void* workspace, int64_t workspaceBytes, cudaStream_t stream);
+
+}  // namespace pda
+#endif

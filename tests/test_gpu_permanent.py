@@ -1,0 +1,105 @@
+"""GPU parity for the matrix permanent and the permanent-based weights.  Floating point, summation
+order differs from the reference by construction: tolerance 1e-9 relative on well-conditioned inputs
+(north_star)."""
+import itertools
+
+import numpy as np
+import pytest
+
+from helpers import golden
+from probabilisticsemslam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+def test_permanent_golden(gpu_api):
+    z = golden("permanent")
+    mats, want = [], []
+    for n in z["dims"]:
+        for i in range(2):
+            mats.append(z[f"A_{n}_{i}"]); want.append(float(z[f"p_{n}_{i}"]))
+    for r, c in z["rect"]:
+        mats.append(z[f"R_{r}_{c}"]); want.append(float(z[f"rp_{r}_{c}"]))
+    got, st = gpu_api.permanent_batch(mats)
+    assert not st.any()
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=0)
+
+
+def test_permanent_definition_and_sanity(gpu_api):
+    assert gpu_api.permanentExact(np.array([[1.0, 2.0], [3.0, 4.0]])) == 10.0
+    assert gpu_api.permanentExact(np.ones((3, 3))) == 6.0
+    assert gpu_api.permanentExact(np.ones((2, 3))) == 6.0      # pad with ones, divide by 1! (nwPerm.cpp:223-230)
+    assert gpu_api.permanentExact(np.array([[2.5]])) == 2.5
+    rng = np.random.default_rng(3)
+    for n in range(1, 8):
+        A = rng.random((n, n))
+        want = sum(np.prod([A[i, p[i]] for i in range(n)]) for p in itertools.permutations(range(n)))
+        np.testing.assert_allclose(gpu_api.permanentExactSquare(A), want, rtol=1e-12)
+    with pytest.raises(RuntimeError):
+        gpu_api.permanentExact(np.ones((33, 33)))                # the reference throws above 32
+
+
+def test_permanent_batch_vs_oracle(gpu_api, oracle):
+    """Config 4 shape: dense U(0,1) square matrices n = 12..20, a batch per n."""
+    for n in (12, 15, 16, 19, 20):
+        A = synth.dense_square(24, n, first=10 * n)
+        got, st = gpu_api.permanent_batch([a.reshape(n, n, order="F") for a in A])
+        _, want = oracle.permanent_batch(A, n, threads=8)
+        assert not st.any()
+        np.testing.assert_allclose(got, want, rtol=RTOL, atol=0)
+
+
+def test_permanent_n24_headline(gpu_api, oracle):
+    A = synth.dense_square(1, 24, first=4242)[0].reshape(24, 24, order="F")
+    want, st = oracle.permanent_exact_square(A)
+    np.testing.assert_allclose(gpu_api.permanentExactSquare(A), want, rtol=RTOL)
+
+
+def test_permanent_range_split_adds_up(gpu_api, oracle):
+    """Gray-range partials over disjoint ranges add up to the whole (the multi-GPU split, config 5)."""
+    n = 22
+    A = synth.dense_square(1, n, first=99)[0].reshape(n, n, order="F")
+    total = 1 << (n - 1)
+    parts = [gpu_api.permanent_range(A, total * r // 8, total * (r + 1) // 8) for r in range(8)]
+    p = sum(h for h, _ in parts) + sum(l for _, l in parts)
+    want, _ = oracle.permanent_exact_square(A)
+    np.testing.assert_allclose((4 * (n & 1) - 2) * p, want, rtol=RTOL)
+    # unaligned ranges are legal too (slower): three uneven pieces
+    cuts = [0, 12345, 1000001, total]
+    parts = [gpu_api.permanent_range(A, cuts[i], cuts[i + 1]) for i in range(3)]
+    p = sum(h for h, _ in parts) + sum(l for _, l in parts)
+    np.testing.assert_allclose((4 * (n & 1) - 2) * p, want, rtol=RTOL)
+
+
+def test_conditioned_permanent(gpu_api):
+    z = golden("conditioned_permanent")
+    n = int(z["n"])
+    got, st = gpu_api.conditioned_permanent_batch([z[f"A{i}"] for i in range(n)], 1)
+    for i in range(n):
+        assert st[i] == int(z[f"s{i}"])
+        np.testing.assert_allclose(got[i], float(z[f"v{i}"]), rtol=RTOL)
+    with pytest.raises(RuntimeError):
+        gpu_api.conditionedPermanent(z["A0"], 7)                 # unknown option throws (assignment.cpp:406)
+
+
+def test_permanent_prob_golden_and_oracle(gpu_api, oracle):
+    z = golden("weights_g2cond")
+    for p in range(int(z["n"])):
+        if f"pp_{p}" in z:
+            np.testing.assert_allclose(gpu_api.permanentProb(z[f"C{p}"], int(z[f"nL{p}"]), 1), z[f"pp_{p}"], rtol=RTOL, atol=1e-300)
+    g2 = synth.g2_gated(80, first=500)
+    cond, _ = gpu_api.condition_costs_batch(g2)
+    keep = [p for p in range(len(cond)) if cond.matrix(p).shape[0] - 1 <= 20]
+    sub = synth.pack([cond.matrix(p) for p in keep], [int(cond.nL[p]) for p in keep])
+    tabs, st = gpu_api.permanent_prob_batch(sub, 1)
+    kb = gpu_api.assignment_prob_batch(sub, 1000)
+    for i in range(len(sub)):
+        s, want = oracle.permanent_prob(sub.matrix(i), int(sub.nL[i]), 1)
+        assert st[i] == s == 0
+        np.testing.assert_allclose(tabs[i], want, rtol=RTOL, atol=1e-300)
+        # accuracy sweep a la comparison.cpp:225-275: permanent weights vs k-best weights
+        assert np.max(np.abs(tabs[i] - kb.prob_table(sub, i))) < 1e-3
+    # single detection: normalised likelihoods
+    C = np.array([[3.0], [7.5], [1.25], [10.0]])
+    np.testing.assert_allclose(gpu_api.permanentProb(C, 3, 1), oracle.permanent_prob(C, 3, 1)[1], rtol=RTOL)

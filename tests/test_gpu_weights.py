@@ -1,0 +1,77 @@
+"""GPU parity for the association weights and the conditioning steps.  Tolerance: 1e-9 relative
+on weights (north_star); conditionCosts is compare/subtract only and must be bit-exact."""
+import numpy as np
+import pytest
+
+from helpers import bits, golden
+from probabilisticsemslam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+def test_condition_costs_bit_exact(gpu_api):
+    z = golden("condition_g2")
+    n = int(z["n"])
+    pb = synth.pack([z[f"in{p}"] for p in range(n)], [30] * n)
+    cond, maps = gpu_api.condition_costs_batch(pb)
+    for p in range(n):
+        np.testing.assert_array_equal(bits(cond.matrix(p)), bits(z[f"out{p}"]))
+        np.testing.assert_array_equal(maps[p], z[f"idx{p}"])
+    out, idx = gpu_api.conditionCosts(z["in3"])
+    np.testing.assert_array_equal(bits(out), bits(z["out3"]))
+
+
+def test_to_probs(gpu_api):
+    z = golden("toprobs")
+    for i in range(int(z["n"])):
+        np.testing.assert_allclose(gpu_api.toProbs(z[f"in{i}"]), z[f"out{i}"], rtol=1e-14, atol=0)
+
+
+def test_assignment_prob_golden(gpu_api):
+    z = golden("probs_appendixA")
+    np.testing.assert_allclose(gpu_api.assignmentProb(z["C"], 3, 30), z["probs"], rtol=RTOL, atol=0)
+    z = golden("probs_config1")
+    for k in (1, 20, 100, 200, 1000):
+        np.testing.assert_allclose(gpu_api.assignmentProb(z["C"], 30, k), z[f"k{k}"], rtol=RTOL, atol=0)
+    z = golden("weights_g1")
+    for p in range(int(z["n"])):
+        np.testing.assert_allclose(gpu_api.assignmentProb(z[f"C{p}"], 30, 200), z[f"k200_{p}"], rtol=RTOL, atol=0)
+
+
+def test_weights_g2_golden(gpu_api):
+    z = golden("weights_g2cond")
+    n = int(z["n"])
+    mats = [z[f"C{p}"] for p in range(n)]
+    pb = synth.pack(mats, [int(z[f"nL{p}"]) for p in range(n)])
+    r200 = gpu_api.assignment_prob_batch(pb, 200)
+    r20 = gpu_api.assignment_prob_batch(pb, 20)
+    for p in range(n):
+        np.testing.assert_allclose(r200.prob_table(pb, p), z[f"k200_{p}"], rtol=RTOL, atol=0)
+        np.testing.assert_allclose(r20.prob_table(pb, p), z[f"k20_{p}"], rtol=RTOL, atol=0)
+        if f"bf_{p}" in z:
+            np.testing.assert_allclose(gpu_api.bruteForceProb(mats[p], int(z[f"nL{p}"])), z[f"bf_{p}"], rtol=RTOL, atol=0)
+
+
+def test_single_detection_and_degenerate(gpu_api, oracle):
+    C = np.array([[3.0], [7.5], [1.25], [50.0], [10.0]])
+    np.testing.assert_allclose(gpu_api.assignmentProb(C, 4, 200), oracle.assignment_prob(C, 4, 200), rtol=RTOL)
+    np.testing.assert_allclose(gpu_api.bruteForceProb(C, 4), oracle.brute_force_prob(C, 4), rtol=RTOL)
+    # no landmarks at all: only the non-assignment column
+    C = np.array([[10.0, np.inf], [np.inf, 10.0]])
+    np.testing.assert_allclose(gpu_api.assignmentProb(C, 0, 10), [[1.0], [1.0]], rtol=0)
+
+
+def test_weights_batch_vs_oracle(gpu_api, oracle):
+    pb = synth.g1_dense(800, first=40_000)
+    got = gpu_api.assignment_prob_batch(pb, 200)
+    want = oracle.batch(pb, 200, threads=8, want_probs=True, want_lists=False)
+    np.testing.assert_allclose(got.probs, want["probs"], rtol=RTOL, atol=0)
+    # and the compMethods relation on gated problems: k-best marginals close to brute-force truth
+    g2 = synth.g2_gated(60, first=77)
+    cond, _ = gpu_api.condition_costs_batch(g2)
+    r = gpu_api.assignment_prob_batch(cond, 200)
+    for p in range(len(cond)):
+        if cond.matrix(p).shape[0] <= 16:
+            truth = oracle.brute_force_prob(cond.matrix(p), int(cond.nL[p]))
+            assert np.max(np.abs(r.prob_table(cond, p) - truth)) < 0.1  # comparison.cpp:319

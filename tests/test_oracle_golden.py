@@ -1,0 +1,121 @@
+"""CPU-only: pins the oracle restatement (oracle/*.c) against vectors produced by the
+reference's own code (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+
+from helpers import KBEST_FILES, assert_kbest_equal, bits, golden, kbest_cases
+
+
+@pytest.mark.parametrize("name", KBEST_FILES)
+def test_kbest_bit_exact(oracle, name):
+    z = golden(name)
+    k, cutoff, use_cut, maxi = int(z["k"]), float(z["cutoff"]), bool(z["use_cutoff"]), bool(z["maximize"])
+    for i, (C, n, r, c, g) in enumerate(kbest_cases(z)):
+        got = oracle.kbest2d_cutoff(k, C, cutoff, maxi) if use_cut else oracle.kbest2d(k, C, maxi)
+        assert_kbest_equal(got, (n, r, c, g), f"{name}[{i}]")
+
+
+def test_appendix_a_known_answer(oracle):
+    # SURVEY.md appendix A, typed in by hand (not read from a file)
+    inf = np.inf
+    C = np.array([[1, 2], [4, 3], [6, 7], [10, inf], [inf, 10]], dtype=np.float64)
+    n, r4c, c4r, g = oracle.kbest2d_cutoff(30, C, 42.0)
+    assert n == 13
+    assert g[:13].tolist() == [4, 6, 8, 8, 9, 11, 11, 12, 13, 14, 16, 17, 20]
+    assert r4c[:13].tolist() == [[0, 1], [1, 0], [0, 2], [2, 0], [2, 1], [1, 2], [0, 4], [3, 0], [3, 1], [1, 4], [2, 4], [3, 2], [3, 4]]
+    assert c4r[6].tolist() == [0, 2, 4, 3, 1] and c4r[12].tolist() == [2, 3, 4, 0, 1]
+    p = oracle.assignment_prob(C, 3, 30)
+    np.testing.assert_allclose(p[0], [0.8629907580527344, 0.11540036124767361, 0.02121833941220368, 0.00039054128738825371], rtol=1e-14)
+    np.testing.assert_allclose(p[1], [0.13038190608964614, 0.85252019571967197, 0.016282059796615539, 0.00081583839406631196], rtol=1e-14)
+
+
+def test_sticky_scratchspace(oracle):
+    z = golden("kbest_sticky_k120")
+    for i in range(int(z["n"])):
+        C = z[f"C{i}"]
+        got = oracle.kbest2d_after_cutoff(int(z["k"]), C, False, C, False, float(z["first_cutoff"]))
+        assert_kbest_equal(got, (int(z[f"n{i}"]), z[f"r{i}"].astype(np.int64), z[f"c{i}"].astype(np.int64), z[f"g{i}"]), f"sticky[{i}]")
+
+
+def test_lap_with_duals(oracle):
+    z = golden("lap")
+    for i in range(int(z["n"])):
+        ret, r4c, c4r, u, v, g = oracle.assign2d(z[f"C{i}"])
+        assert ret == int(z[f"ret{i}"])
+        np.testing.assert_array_equal(r4c, z[f"r{i}"]); np.testing.assert_array_equal(c4r, z[f"c{i}"])
+        np.testing.assert_array_equal(bits(u), bits(z[f"u{i}"])); np.testing.assert_array_equal(bits(v), bits(z[f"v{i}"]))
+        assert bits([g])[0] == bits([float(z[f"g{i}"])])[0]
+        ret, r4c, c4r, u, v, g, fb = oracle.shortest_path(z[f"S{i}"])
+        assert ret == int(z[f"sret{i}"])
+        np.testing.assert_array_equal(r4c, z[f"sr{i}"]); np.testing.assert_array_equal(c4r, z[f"sc{i}"])
+        np.testing.assert_array_equal(bits(u), bits(z[f"su{i}"])); np.testing.assert_array_equal(bits(v), bits(z[f"sv{i}"]))
+        np.testing.assert_array_equal(fb, z[f"sf{i}"])
+
+
+def test_condition_costs(oracle):
+    z = golden("condition_g2")
+    for p in range(int(z["n"])):
+        out, idx = oracle.condition_costs(z[f"in{p}"])
+        np.testing.assert_array_equal(bits(out), bits(z[f"out{p}"]))
+        np.testing.assert_array_equal(idx, z[f"idx{p}"])
+
+
+def test_weights(oracle):
+    # exp() comes from the host libm in both the reference and the oracle: allow last-bit drift only
+    z = golden("weights_g2cond")
+    for p in range(int(z["n"])):
+        C, nL = z[f"C{p}"], int(z[f"nL{p}"])
+        np.testing.assert_allclose(oracle.assignment_prob(C, nL, 200), z[f"k200_{p}"], rtol=1e-13, atol=0)
+        np.testing.assert_allclose(oracle.assignment_prob(C, nL, 20), z[f"k20_{p}"], rtol=1e-13, atol=0)
+        if f"bf_{p}" in z:
+            np.testing.assert_allclose(oracle.brute_force_prob(C, nL), z[f"bf_{p}"], rtol=1e-13, atol=0)
+            st, pp = oracle.permanent_prob(C, nL, 1)
+            assert st == 0
+            np.testing.assert_allclose(pp, z[f"pp_{p}"], rtol=1e-13, atol=0)
+    z = golden("weights_g1")
+    for p in range(int(z["n"])):
+        np.testing.assert_allclose(oracle.assignment_prob(z[f"C{p}"], 30, 200), z[f"k200_{p}"], rtol=1e-13, atol=0)
+    z = golden("probs_config1")
+    for k in (1, 20, 100, 200, 1000):
+        np.testing.assert_allclose(oracle.assignment_prob(z["C"], 30, k), z[f"k{k}"], rtol=1e-13, atol=0)
+    z = golden("toprobs")
+    for i in range(int(z["n"])):
+        np.testing.assert_allclose(oracle.to_probs(z[f"in{i}"]), z[f"out{i}"], rtol=1e-14, atol=0)
+
+
+def test_permanents(oracle):
+    z = golden("permanent")
+    for n in z["dims"]:
+        for i in range(2):
+            val, st = oracle.permanent_exact_square(z[f"A_{n}_{i}"])
+            assert st == 0 and bits([val])[0] == bits([float(z[f"p_{n}_{i}"])])[0], (n, i)
+    for r, c in z["rect"]:
+        val, st = oracle.permanent_exact(z[f"R_{r}_{c}"])
+        assert st == 0 and bits([val])[0] == bits([float(z[f"rp_{r}_{c}"])])[0], (r, c)
+    assert oracle.permanent_exact_square(np.ones((33, 33)))[1] == 1  # the reference throws above 32
+    assert oracle.permanent_exact_square(np.array([[1.0, 2.0], [3.0, 4.0]]))[0] == 10.0
+    assert oracle.permanent_exact(np.ones((2, 3)))[0] == 6.0
+    z = golden("conditioned_permanent")
+    for i in range(int(z["n"])):
+        val, st = oracle.conditioned_permanent(z[f"A{i}"], 1)
+        assert st == int(z[f"s{i}"])
+        np.testing.assert_allclose(val, float(z[f"v{i}"]), rtol=1e-14)
+
+
+def test_permanent_small_vs_definition(oracle):
+    # independent of any file: permanent by brute-force enumeration of permutations
+    import itertools
+    rng = np.random.default_rng(5)
+    for n in range(1, 8):
+        A = rng.random((n, n))
+        want = sum(np.prod([A[i, p[i]] for i in range(n)]) for p in itertools.permutations(range(n)))
+        np.testing.assert_allclose(oracle.permanent_exact_square(A)[0], want, rtol=1e-12)
+
+
+def test_kbest_marginals_approach_brute_force(oracle):
+    # the compMethods relation (comparison.cpp:261-275, 319-324): k-best marginals ~ brute-force marginals
+    z = golden("weights_g2cond")
+    for p in range(int(z["n"])):
+        if f"bf_{p}" in z:
+            assert np.max(np.abs(z[f"k200_{p}"] - z[f"bf_{p}"])) < 0.1
+            assert np.max(np.abs(z[f"pp_{p}"] - z[f"bf_{p}"])) < 1e-6
