@@ -53,6 +53,9 @@ extern "C" {
 int pda_version(void);
 const char* pda_last_error(void);
 int pda_device_count(void);
+/* Diagnostic: measured FP64 FMA throughput of the current device in TFLOP/s (a DFMA micro-benchmark;
+ * the denominator of the permanent kernel's roofline). Negative on failure. */
+double pda_diag_dfma_tflops(void);
 
 /* ------------------------------------------------------------------------------------------
  * Murty k-best enumeration (+ optional fused association weights), one warp per problem.

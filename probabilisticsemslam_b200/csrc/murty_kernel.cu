@@ -82,46 +82,63 @@ struct Node {
     int r4c[R];    // row of each owned column (-1 = free)
 };
 
+// One relaxation pass of the row scan from column `cur` (shortestPathCPP.cpp:179-195 / 307-325) over
+// the rows flagged in `act`, followed by the lane-local first minimum.  REAL = the column exists in
+// sm.C; otherwise it is one of the reference's zero padding columns, C == +0.0 and delta + 0.0 == delta
+// (delta is never -0.0: the staged matrix holds no -0.0 and x - x rounds to +0.0).
+template <int R, bool REAL>
+__device__ __forceinline__ void relax(const double* __restrict__ Ccol, const double delta, const double ucur,
+                                      const double (&v)[R], const unsigned act, const int cur,
+                                      double (&cand)[R], int (&pred)[R], const int lane) {
+    const double du = delta - ucur;  // used by the padding-column form only
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+        const bool a = (act >> s) & 1u;
+        double t;
+        if (REAL) {
+            const double c = a ? Ccol[lane + 32 * s] : 0.0;
+            t = ((delta + c) - ucur) - v[s];
+        } else {
+            t = du - v[s];
+        }
+        const bool better = a && (t < cand[s]);
+        cand[s] = better ? t : cand[s];
+        pred[s] = better ? cur : pred[s];
+    }
+}
+
 // One shortest augmenting path from `startCol` over the rows flagged in scanBits
 // (bit s = row lane+32s), then the dual update and the flip along the path.
 //   shortestPathCPP.cpp:168-226 / 297-356 (scan), :92-106 (duals), :108-116 (flip).
 // forbBits hides rows on the first hop only (:310).  numColReal = columns that exist in
 // sm.C; columns beyond are the reference's zero padding.  Returns true if infeasible.
+//
+// cand[s] is the reference's shortestPathCost for a row that is still to be scanned and +inf for
+// every other row (scanned rows park their final cost in done[s]), so the warp arg-min needs no mask.
 template <int R>
 __device__ __forceinline__ bool augment_from(const int startCol, const int numColReal, const int ld,
                                              const WarpSmem& sm, Node<R>& nd, unsigned scanBits,
                                              const unsigned forbBits, const int lane) {
-    double spc[R];
+    double cand[R], done[R];
     int pred[R];
-    unsigned colSeen[R];
 #pragma unroll
-    for (int s = 0; s < R; ++s) { spc[s] = CUDART_INF; pred[s] = 0; colSeen[s] = 0u; }
+    for (int s = 0; s < R; ++s) { cand[s] = CUDART_INF; done[s] = 0.0; pred[s] = 0; }
     unsigned scannedBits = 0u;
-    unsigned hide = forbBits;  // cleared after the first hop
     int cur = startCol, sink;
     double delta = 0.0;
+    bool first = true;
 
     for (;;) {
-#pragma unroll
-        for (int s = 0; s < R; ++s)
-            if ((cur >> 5) == s) colSeen[s] |= 1u << (cur & 31);
         const double ucur = sm.u[cur];
-        const bool real = cur < numColReal;
-        const double* Ccol = sm.C + cur * ld;
-        double best = CUDART_INF;
+        const unsigned act = first ? (scanBits & ~forbBits) : scanBits;
+        first = false;
+        if (cur < numColReal) relax<R, true>(sm.C + cur * ld, delta, ucur, nd.v, act, cur, cand, pred, lane);
+        else relax<R, false>(nullptr, delta, ucur, nd.v, act, cur, cand, pred, lane);
+        // lane-local first minimum (lower slot = lower row wins ties), then the warp arg-min
+        double best = cand[0];
         int bs = 0;
-        const unsigned act = scanBits & ~hide;
 #pragma unroll
-        for (int s = 0; s < R; ++s) {
-            if ((act >> s) & 1u) {
-                const double c = real ? Ccol[lane + 32 * s] : 0.0;
-                const double red = ((delta + c) - ucur) - nd.v[s];
-                if (red < spc[s]) { spc[s] = red; pred[s] = cur; }
-                if (spc[s] < best) { best = spc[s]; bs = s; }
-            }
-        }
-        hide = 0u;
-        best = best + 0.0;  // -0.0 and +0.0 compare equal in the reference; give them one key
+        for (int s = 1; s < R; ++s) if (cand[s] < best) { best = cand[s]; bs = s; }
         unsigned khi, klo;
         to_key(best, khi, klo);
         const unsigned mhi = __reduce_min_sync(FULL, khi);
@@ -134,7 +151,10 @@ __device__ __forceinline__ bool augment_from(const int startCol, const int numCo
         int mine = nd.c4r[0];
 #pragma unroll
         for (int s = 0; s < R; ++s) {
-            if (lane + 32 * s == closest) { scanBits &= ~(1u << s); scannedBits |= 1u << s; }
+            if (lane + 32 * s == closest) {
+                done[s] = delta; cand[s] = CUDART_INF;
+                scanBits &= ~(1u << s); scannedBits |= 1u << s;
+            }
             if (s > 0 && (closest >> 5) == s) mine = nd.c4r[s];
         }
         const int next = __shfl_sync(FULL, mine, closest & 31);
@@ -142,22 +162,30 @@ __device__ __forceinline__ bool augment_from(const int startCol, const int numCo
         cur = next;
     }
 
-    // duals, using row4col as it was before the flip (:92-106)
+    // duals, using row4col as it was before the flip (:92-106).  A column other than startCol was scanned
+    // exactly when the row it is paired with was scanned (the sink row is unpaired).
+    unsigned rowsDone[R];
 #pragma unroll
     for (int s = 0; s < R; ++s) {
-        if ((scannedBits >> s) & 1u) nd.v[s] = (nd.v[s] - delta) + spc[s];
-        sm.spc[lane + 32 * s] = spc[s];
+        const bool sc = (scannedBits >> s) & 1u;
+        rowsDone[s] = __ballot_sync(FULL, sc);
+        if (sc) nd.v[s] = (nd.v[s] - delta) + done[s];
+        sm.spc[lane + 32 * s] = done[s];
         sm.pred[lane + 32 * s] = (short)pred[s];
     }
     __syncwarp();
 #pragma unroll
     for (int s = 0; s < R; ++s) {
-        if ((colSeen[s] >> lane) & 1u) {
-            const int c = lane + 32 * s;
-            if (c == startCol) nd.u[s] = nd.u[s] + delta;
-            else nd.u[s] = (nd.u[s] + delta) - sm.spc[nd.r4c[s]];
-            sm.u[c] = nd.u[s];
+        const int c = lane + 32 * s, r = nd.r4c[s];
+        bool seen = false;
+        if (r >= 0) {
+            unsigned w = rowsDone[0];
+#pragma unroll
+            for (int q = 1; q < R; ++q) if ((r >> 5) == q) w = rowsDone[q];
+            seen = (w >> (r & 31)) & 1u;
         }
+        if (c == startCol) { nd.u[s] = nd.u[s] + delta; sm.u[c] = nd.u[s]; }
+        else if (seen) { nd.u[s] = (nd.u[s] + delta) - sm.spc[r]; sm.u[c] = nd.u[s]; }
     }
     // flip along the predecessor chain (:108-116); sm.r4c still holds the pre-flip pairing
     int r = sink, c;
@@ -275,7 +303,7 @@ __device__ __forceinline__ void publish_cols(const WarpSmem& sm, const Node<R>& 
 __device__ __forceinline__ double stage_safe_matrix(const double* Cg, double* Cs, const int numEl,
                                                     const bool maximize, const bool makeSafe, const int lane) {
     if (!makeSafe) {
-        for (int i = lane; i < numEl; i += 32) Cs[i] = Cg[i];
+        for (int i = lane; i < numEl; i += 32) Cs[i] = Cg[i] + 0.0;  // + 0.0: no -0.0 in the staged matrix
         __syncwarp();
         return 0.0;
     }
@@ -284,12 +312,12 @@ __device__ __forceinline__ double stage_safe_matrix(const double* Cg, double* Cs
         d = CUDART_INF;
         for (int i = lane; i < numEl; i += 32) { const double x = Cg[i]; d = (x < d) ? x : d; }
         d = warp_min(d);
-        for (int i = lane; i < numEl; i += 32) Cs[i] = Cg[i] - d;
+        for (int i = lane; i < numEl; i += 32) Cs[i] = (Cg[i] - d) + 0.0;
     } else {
         d = -CUDART_INF;
         for (int i = lane; i < numEl; i += 32) { const double x = Cg[i]; d = (d < x) ? x : d; }
         d = warp_max(d);
-        for (int i = lane; i < numEl; i += 32) Cs[i] = -Cg[i] + d;
+        for (int i = lane; i < numEl; i += 32) Cs[i] = (-Cg[i] + d) + 0.0;
     }
     __syncwarp();
     return d;

@@ -54,7 +54,45 @@ std::vector<DevArena> g_arenas;
 
 using namespace pda;
 
+// FP64 pipe micro-benchmark: 8 independent DFMA chains per thread (diagnostic; gives the measured
+// denominator for the permanent kernel's roofline, which MEASURED_PEAKS.json does not carry).
+__global__ void dfma_peak_kernel(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3;
+    double a4 = a0 + 4e-3, a5 = a0 + 5e-3, a6 = a0 + 6e-3, a7 = a0 + 7e-3;
+    const double b = 0.999999, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
 extern "C" {
+
+double pda_diag_dfma_tflops(void) {
+    DeviceInfo dev;
+    if (current_device_info(&dev)) return -1.0;
+    const int ctas = dev.smCount * 8, threads = 256, iters = 8192;
+    double* out = nullptr;
+    if (cudaMalloc(&out, (size_t)ctas * threads * 8) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    dfma_peak_kernel<<<ctas, threads>>>(out, iters);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        dfma_peak_kernel<<<ctas, threads>>>(out, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double tf = 2.0 * 8.0 * iters * (double)ctas * threads / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    return cudaGetLastError() == cudaSuccess ? best : -1.0;
+}
 
 int pda_version(void) { return 100; }
 const char* pda_last_error(void) { return g_err; }

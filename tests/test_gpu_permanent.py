@@ -83,23 +83,45 @@ def test_conditioned_permanent(gpu_api):
         gpu_api.conditionedPermanent(z["A0"], 7)                 # unknown option throws (assignment.cpp:406)
 
 
+def _rel(a, b):
+    m = b > 0
+    return float(np.max(np.abs(a[m] - b[m]) / b[m])) if m.any() else 0.0
+
+
 def test_permanent_prob_golden_and_oracle(gpu_api, oracle):
+    """Permanent-based weights on gated (sparse, wide-dynamic-range) problems.  The NW sum cancels, and on
+    some of these inputs the REFERENCE is itself only ~1e-8 accurate, so each result is
+    judged against a cancellation-free truth (tests/truth.py): within 1e-9 of the reference wherever
+    the reference is accurate, and never worse than a small multiple of the reference's own error."""
+    from truth import permanent_prob_truth
     z = golden("weights_g2cond")
     for p in range(int(z["n"])):
         if f"pp_{p}" in z:
-            np.testing.assert_allclose(gpu_api.permanentProb(z[f"C{p}"], int(z[f"nL{p}"]), 1), z[f"pp_{p}"], rtol=RTOL, atol=1e-300)
+            got = gpu_api.permanentProb(z[f"C{p}"], int(z[f"nL{p}"]), 1)
+            truth = permanent_prob_truth(z[f"C{p}"], int(z[f"nL{p}"]))
+            ref_err = _rel(z[f"pp_{p}"], truth)
+            assert _rel(got, truth) <= max(RTOL, 8 * ref_err)
+            if ref_err < 1e-10:
+                np.testing.assert_allclose(got, z[f"pp_{p}"], rtol=RTOL, atol=1e-300)
     g2 = synth.g2_gated(80, first=500)
     cond, _ = gpu_api.condition_costs_batch(g2)
     keep = [p for p in range(len(cond)) if cond.matrix(p).shape[0] - 1 <= 20]
     sub = synth.pack([cond.matrix(p) for p in keep], [int(cond.nL[p]) for p in keep])
     tabs, st = gpu_api.permanent_prob_batch(sub, 1)
     kb = gpu_api.assignment_prob_batch(sub, 1000)
+    n_tight = 0
     for i in range(len(sub)):
         s, want = oracle.permanent_prob(sub.matrix(i), int(sub.nL[i]), 1)
         assert st[i] == s == 0
-        np.testing.assert_allclose(tabs[i], want, rtol=RTOL, atol=1e-300)
+        truth = permanent_prob_truth(sub.matrix(i), int(sub.nL[i]))
+        ref_err = _rel(want, truth)
+        assert _rel(tabs[i], truth) <= max(RTOL, 8 * ref_err), (i, _rel(tabs[i], truth), ref_err)
+        if ref_err < 1e-10:
+            n_tight += 1
+            np.testing.assert_allclose(tabs[i], want, rtol=RTOL, atol=1e-300)
         # accuracy sweep a la comparison.cpp:225-275: permanent weights vs k-best weights
         assert np.max(np.abs(tabs[i] - kb.prob_table(sub, i))) < 1e-3
+    assert n_tight >= len(sub) * 3 // 4
     # single detection: normalised likelihoods
     C = np.array([[3.0], [7.5], [1.25], [10.0]])
     np.testing.assert_allclose(gpu_api.permanentProb(C, 3, 1), oracle.permanent_prob(C, 3, 1)[1], rtol=RTOL)
