@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpda_b200.so")
+LIB_PATH = os.environ.get("PDA_B200_LIB", os.path.join(_HERE, "libpda_b200.so"))  # override: A/B builds while tuning
 
 i32, i64, u64, dbl, ptr = C.c_int32, C.c_int64, C.c_uint64, C.c_double, C.c_void_p
 

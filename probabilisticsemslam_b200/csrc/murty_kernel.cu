@@ -33,6 +33,11 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 
+// resident CTAs per SM the register allocator must leave room for (4 warps each)
+#ifndef PDA_MURTY_MINB
+#define PDA_MURTY_MINB 6
+#endif
+
 struct __align__(16) HeapEntry {
     double gain;
     int node;
@@ -71,6 +76,7 @@ struct WarpSmem {
     double* acc;     // [numCol * (nL+1)] weight accumulators
     short* r4c;      // [32R] mirror of the working node's row4col
     short* pred;     // [32R] predecessor column per row
+    unsigned short* c4r;  // [32R] mirror of the working node's col4row (0xffff = free)
 };
 
 // The working node, distributed over the warp.
@@ -82,26 +88,26 @@ struct Node {
     int r4c[R];    // row of each owned column (-1 = free)
 };
 
-// One relaxation pass of the row scan from column `cur` (shortestPathCPP.cpp:179-195 / 307-325) over
-// the rows flagged in `act`, followed by the lane-local first minimum.  REAL = the column exists in
-// sm.C; otherwise it is one of the reference's zero padding columns, C == +0.0 and delta + 0.0 == delta
-// (delta is never -0.0: the staged matrix holds no -0.0 and x - x rounds to +0.0).
+// One relaxation pass of the row scan from column `cur` (shortestPathCPP.cpp:179-195 / 307-325).
+// Rows that must not take part carry v == -inf, which makes their reduced cost +inf, so no row mask is
+// needed: `t < cand` is simply never true for them.  REAL = the column exists in sm.C; otherwise it is
+// one of the reference's zero padding columns, C == +0.0 and delta + 0.0 == delta (delta is never -0.0:
+// the staged matrix holds no -0.0 and x - x rounds to +0.0).
 template <int R, bool REAL>
-__device__ __forceinline__ void relax(const double* __restrict__ Ccol, const double delta, const double ucur,
-                                      const double (&v)[R], const unsigned act, const int cur,
+__device__ __forceinline__ void relax(const double* __restrict__ Ccol, const int n, const double delta,
+                                      const double ucur, const double (&v)[R], const int cur,
                                       double (&cand)[R], int (&pred)[R], const int lane) {
     const double du = delta - ucur;  // used by the padding-column form only
 #pragma unroll
     for (int s = 0; s < R; ++s) {
-        const bool a = (act >> s) & 1u;
         double t;
         if (REAL) {
-            const double c = a ? Ccol[lane + 32 * s] : 0.0;
+            const double c = (lane + 32 * s < n) ? Ccol[lane + 32 * s] : 0.0;
             t = ((delta + c) - ucur) - v[s];
         } else {
             t = du - v[s];
         }
-        const bool better = a && (t < cand[s]);
+        const bool better = t < cand[s];
         cand[s] = better ? t : cand[s];
         pred[s] = better ? cur : pred[s];
     }
@@ -113,53 +119,59 @@ __device__ __forceinline__ void relax(const double* __restrict__ Ccol, const dou
 // forbBits hides rows on the first hop only (:310).  numColReal = columns that exist in
 // sm.C; columns beyond are the reference's zero padding.  Returns true if infeasible.
 //
-// cand[s] is the reference's shortestPathCost for a row that is still to be scanned and +inf for
-// every other row (scanned rows park their final cost in done[s]), so the warp arg-min needs no mask.
+// cand[s] is the reference's shortestPathCost of a row that is still to be scanned.  Rows outside the
+// scan set keep cand == +inf (their v is -inf, so they never relax); a row that HAS been scanned gets
+// its cand poisoned to NaN (one high-word write): `t < NaN` is false, so it never relaxes again, the
+// arg-min skips it, and "scanned" can be read back from it afterwards.  The cost at which a row was
+// scanned (== delta at that moment) is parked in sm.spc by lane 0, where the dual update reads it.
+constexpr int NAN_HI = 0x7ff80000;
+
 template <int R>
 __device__ __forceinline__ bool augment_from(const int startCol, const int numColReal, const int ld,
-                                             const WarpSmem& sm, Node<R>& nd, unsigned scanBits,
+                                             const WarpSmem& sm, Node<R>& nd, const unsigned scanBits,
                                              const unsigned forbBits, const int lane) {
-    double cand[R], done[R];
+    double cand[R], vEff[R];
     int pred[R];
 #pragma unroll
-    for (int s = 0; s < R; ++s) { cand[s] = CUDART_INF; done[s] = 0.0; pred[s] = 0; }
-    unsigned scannedBits = 0u;
+    for (int s = 0; s < R; ++s) {
+        cand[s] = CUDART_INF;
+        pred[s] = 0;
+        vEff[s] = ((scanBits >> s) & 1u) ? nd.v[s] : -CUDART_INF;
+    }
     int cur = startCol, sink;
     double delta = 0.0;
-    bool first = true;
-
-    for (;;) {
+    {   // first hop: the forbidden rows sit this one out (:310)
+        double vHop[R];
+#pragma unroll
+        for (int s = 0; s < R; ++s) vHop[s] = ((forbBits >> s) & 1u) ? -CUDART_INF : vEff[s];
         const double ucur = sm.u[cur];
-        const unsigned act = first ? (scanBits & ~forbBits) : scanBits;
-        first = false;
-        if (cur < numColReal) relax<R, true>(sm.C + cur * ld, delta, ucur, nd.v, act, cur, cand, pred, lane);
-        else relax<R, false>(nullptr, delta, ucur, nd.v, act, cur, cand, pred, lane);
-        // lane-local first minimum (lower slot = lower row wins ties), then the warp arg-min
+        if (cur < numColReal) relax<R, true>(sm.C + cur * ld, ld, delta, ucur, vHop, cur, cand, pred, lane);
+        else relax<R, false>(nullptr, ld, delta, ucur, vHop, cur, cand, pred, lane);
+    }
+    for (;;) {
+        // lane-local first minimum (lower slot = lower row wins ties; NaN = already scanned), then the warp arg-min
         double best = cand[0];
         int bs = 0;
 #pragma unroll
-        for (int s = 1; s < R; ++s) if (cand[s] < best) { best = cand[s]; bs = s; }
+        for (int s = 1; s < R; ++s) if (cand[s] < best || best != best) { best = cand[s]; bs = s; }
         unsigned khi, klo;
         to_key(best, khi, klo);
         const unsigned mhi = __reduce_min_sync(FULL, khi);
+        if (mhi >= KEY_INF_HI) return true;  // minVal == +inf (:197, :327): nothing finite is left
         const unsigned mlo = __reduce_min_sync(FULL, (khi == mhi) ? klo : 0xffffffffu);
-        if (mhi == KEY_INF_HI && mlo == 0u) return true;  // minVal == +inf (:197, :327)
         const bool win = (khi == mhi) && (klo == mlo);
         const int closest = (int)__reduce_min_sync(FULL, win ? (unsigned)(lane + 32 * bs) : 0xffffu);
         delta = from_key(mhi, mlo);
-
-        int mine = nd.c4r[0];
+        if (lane == 0) sm.spc[closest] = delta;
 #pragma unroll
-        for (int s = 0; s < R; ++s) {
-            if (lane + 32 * s == closest) {
-                done[s] = delta; cand[s] = CUDART_INF;
-                scanBits &= ~(1u << s); scannedBits |= 1u << s;
-            }
-            if (s > 0 && (closest >> 5) == s) mine = nd.c4r[s];
-        }
-        const int next = __shfl_sync(FULL, mine, closest & 31);
-        if (next < 0) { sink = closest; break; }
-        cur = next;
+        for (int s = 0; s < R; ++s)
+            if (lane + 32 * s == closest) cand[s] = __hiloint2double(NAN_HI, __double2loint(cand[s]));
+        const unsigned next = sm.c4r[closest];
+        if (next == 0xffffu) { sink = closest; break; }
+        cur = (int)next;
+        const double ucur = sm.u[cur];
+        if (cur < numColReal) relax<R, true>(sm.C + cur * ld, ld, delta, ucur, vEff, cur, cand, pred, lane);
+        else relax<R, false>(nullptr, ld, delta, ucur, vEff, cur, cand, pred, lane);
     }
 
     // duals, using row4col as it was before the flip (:92-106).  A column other than startCol was scanned
@@ -167,15 +179,13 @@ __device__ __forceinline__ bool augment_from(const int startCol, const int numCo
     unsigned rowsDone[R];
 #pragma unroll
     for (int s = 0; s < R; ++s) {
-        const bool sc = (scannedBits >> s) & 1u;
-        rowsDone[s] = __ballot_sync(FULL, sc);
-        if (sc) nd.v[s] = (nd.v[s] - delta) + done[s];
-        sm.spc[lane + 32 * s] = done[s];
+        rowsDone[s] = __ballot_sync(FULL, __double2hiint(cand[s]) == NAN_HI);
         sm.pred[lane + 32 * s] = (short)pred[s];
     }
     __syncwarp();
 #pragma unroll
     for (int s = 0; s < R; ++s) {
+        if ((rowsDone[s] >> lane) & 1u) nd.v[s] = (nd.v[s] - delta) + sm.spc[lane + 32 * s];
         const int c = lane + 32 * s, r = nd.r4c[s];
         bool seen = false;
         if (r >= 0) {
@@ -201,7 +211,10 @@ __device__ __forceinline__ bool augment_from(const int startCol, const int numCo
     } while (c != startCol);
     __syncwarp();
 #pragma unroll
-    for (int s = 0; s < R; ++s) sm.r4c[lane + 32 * s] = (short)nd.r4c[s];
+    for (int s = 0; s < R; ++s) {
+        sm.r4c[lane + 32 * s] = (short)nd.r4c[s];
+        sm.c4r[lane + 32 * s] = (unsigned short)nd.c4r[s];
+    }
     __syncwarp();
     return false;
 }
@@ -295,6 +308,7 @@ __device__ __forceinline__ void publish_cols(const WarpSmem& sm, const Node<R>& 
     for (int s = 0; s < R; ++s) {
         sm.u[lane + 32 * s] = nd.u[s];
         sm.r4c[lane + 32 * s] = (short)nd.r4c[s];
+        sm.c4r[lane + 32 * s] = (unsigned short)nd.c4r[s];
     }
     __syncwarp();
 }
@@ -457,6 +471,8 @@ __device__ void solve_problem(const MurtyArgs& a, const long long p, const WarpS
                 if (lane + 32 * s == c) nd.r4c[s] = -1;
             }
             if (c == a0) hideFirst = parForb;  // first child inherits every constraint on the active column (:490)
+            if (lane == 0) sm.c4r[r0] = 0xffffu;  // the freed row is the only sink of this search
+            __syncwarp();
             const bool infeasible = augment_from<R>(c, nc, n, sm, nd, inPar, hideFirst, lane);
             if (!infeasible) {
                 const double g = path_gain(sm, n, nc);
@@ -518,11 +534,12 @@ __device__ __forceinline__ WarpSmem carve(unsigned char* base, const MurtyGeomet
     sm.acc = sm.spc + D;
     sm.r4c = reinterpret_cast<short*>(sm.acc + g.pCap);
     sm.pred = sm.r4c + D;
+    sm.c4r = reinterpret_cast<unsigned short*>(sm.pred + D);
     return sm;
 }
 
 template <int R>
-__global__ void murty_kernel(const MurtyArgs a) {
+__global__ void __launch_bounds__(128, PDA_MURTY_MINB) murty_kernel(const MurtyArgs a) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -615,7 +632,7 @@ int murty_geometry(int32_t k, int32_t maxNumRow, int32_t maxNumCol, bool weights
     g->arenaStride = (g->heapBytes + nodes * g->nodeStride + 255) / 256 * 256;
     g->cCap = round_up(maxNumRow * maxNumCol, 2);
     g->pCap = weights ? round_up(maxNumCol * maxNumRow, 2) : 0;
-    g->smemPerWarp = round_up(8 * (g->cCap + g->pCap + 2 * D) + 2 * 2 * D, 16);
+    g->smemPerWarp = round_up(8 * (g->cCap + g->pCap + 2 * D) + 3 * 2 * D, 16);
     if (g->smemPerWarp > dev.maxSmemOptin)
         return fail(PDA_ERR_UNSUPPORTED, "murty: a %d x %d problem needs %d B of shared memory per warp (limit %d)",
                     maxNumRow, maxNumCol, g->smemPerWarp, dev.maxSmemOptin);
@@ -654,7 +671,7 @@ template <int R>
 static int launch_lap_r(const LapArgs& a, cudaStream_t stream, const DeviceInfo& dev) {
     const int D = 32 * R;
     const int cCap = round_up(a.maxNumRow * a.maxNumCol, 2);
-    const int smemPerWarp = round_up(8 * (cCap + 2 * D) + 4 * D, 16);
+    const int smemPerWarp = round_up(8 * (cCap + 2 * D) + 6 * D, 16);
     if (smemPerWarp > dev.maxSmemOptin) return fail(PDA_ERR_UNSUPPORTED, "lap: matrix too large for shared memory");
     int wpc = 4;
     while (wpc > 1 && wpc * smemPerWarp > dev.maxSmemOptin) wpc >>= 1;
