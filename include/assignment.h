@@ -1,0 +1,48 @@
+/* assignment.h -- drop-in replacement for the numeric half of the reference's assignment.h
+ * (reference: assignment.h:11-43; assignment.cpp:145-290 permanentProb, :325-435 conditionedPermanent,
+ * :439-525 conditionCosts, :527-542 toProbs, :547-683 assignmentProb, :835-964 bruteForceProb).
+ * Same names, same std::vector-based signatures, same return shapes: probs[nM][nL+1], the last entry
+ * of each row being the non-assignment probability.  Everything runs as a batch of one on the B200
+ * through libpda_b200.so; the *Batch forms underneath are what a multi-frame caller should use.
+ *
+ * Not here: the GTSAM / OpenCV typed entry points of the reference header (getAssignmentProbs, asgnBB,
+ * computeQuadricCostMatrix, computeBBCostMatrix, getMeans, getCovs, saveAssignmentProb).  They only build
+ * cost matrices and then call the functions below; keep the reference's definitions for them.
+ */
+#ifndef sensSLAM_assignment
+#define sensSLAM_assignment
+
+#include <stddef.h>
+
+#include <vector>
+
+#include "nwPerm.h"
+
+std::vector<std::vector<double> > assignmentProb(const std::vector<double>& costMatrix, size_t nL, size_t nM, size_t k);
+
+/* permOpt: 1 exact, 2 "long" (same double kernel, as in the reference); 0 (Huber approximation) and anything
+ * else throw std::runtime_error. */
+std::vector<std::vector<double> > permanentProb(std::vector<double> costMatrix, size_t nL, size_t nM, int permOpt);
+
+std::vector<std::vector<double> > bruteForceProb(const std::vector<double>& costMatrix, size_t nL, size_t nM);
+
+std::vector<double> conditionCosts(const std::vector<double>& costs, size_t nRows, size_t nCols,
+                                   std::vector<ptrdiff_t>& rowIdxOut);
+
+void toProbs(std::vector<double>& costMatrix);
+
+/* raw form of conditionedPermanent: A is rows x cols, column-major */
+double conditionedPermanentRaw(const double* A, size_t rows, size_t cols, int permOpt);
+#ifdef PDA_HAVE_EIGEN
+inline double conditionedPermanent(const Eigen::MatrixXd& A, int permOpt) {
+    return conditionedPermanentRaw(A.data(), size_t(A.rows()), size_t(A.cols()), permOpt);
+}
+#endif
+
+/* ---- batch forms (one call, many frames): what the GPU is built for --------------------------------
+ * costs[p] is problem p's column-major (nL[p]+nM[p]) x nM[p] matrix. Returns probs[p][m][l]. */
+std::vector<std::vector<std::vector<double> > > assignmentProbBatch(const std::vector<std::vector<double> >& costs,
+                                                                    const std::vector<size_t>& nL,
+                                                                    const std::vector<size_t>& nM, size_t k);
+
+#endif

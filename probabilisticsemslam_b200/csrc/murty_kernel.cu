@@ -639,10 +639,27 @@ int murty_geometry(int32_t k, int32_t maxNumRow, int32_t maxNumCol, bool weights
     int wpc = 4;
     while (wpc > 1 && wpc * g->smemPerWarp > dev.maxSmemOptin) wpc >>= 1;
     g->warpsPerCta = wpc;
-    // resident CTAs per SM: bounded by shared memory (227 KB usable, ~1 KB reserved per CTA) and by 32 warps/SM
-    int byS = (227 * 1024) / (wpc * g->smemPerWarp + 1024);
-    int byW = 32 / wpc;
-    g->ctasPerSm = byS < 1 ? 1 : (byS < byW ? byS : byW);
+    // resident CTAs per SM, as the occupancy calculator sees this instantiation (registers, shared memory)
+    int occ = 0;
+    const int threads = 32 * wpc;
+    const size_t smem = (size_t)wpc * g->smemPerWarp;
+    cudaError_t e = cudaSuccess;
+    switch (g->R) {
+        case 1:
+            e = cudaFuncSetAttribute(murty_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, murty_kernel<1>, threads, smem);
+            break;
+        case 2:
+            e = cudaFuncSetAttribute(murty_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, murty_kernel<2>, threads, smem);
+            break;
+        default:
+            e = cudaFuncSetAttribute(murty_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, murty_kernel<4>, threads, smem);
+            break;
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "occupancy query for murty_kernel");
+    g->ctasPerSm = occ < 1 ? 1 : occ;
     return PDA_OK;
 }
 

@@ -1,0 +1,151 @@
+// assignment_shim.cpp -- the reference's assignment.h numeric entry points (assignment.cpp:145-290,
+// 325-435, 439-525, 527-542, 547-683, 835-964) and nwPerm.h exact permanents (nwPerm.cpp:217-231,
+// 251-332, 386-400) as batch-of-one calls into libpda_b200.so.  Marshalling only.
+#include "assignment.h"
+
+#include <math.h>
+#include <stdint.h>
+
+#include <limits>
+#include <stdexcept>
+#include <string>
+
+#include "pda_b200.h"
+
+void pdaCheck(int rc, const char* where);
+int pdaShimDevice();
+
+static std::vector<std::vector<double> > unflatten(const std::vector<double>& flat, size_t nM, size_t width) {
+    std::vector<std::vector<double> > out(nM, std::vector<double>(width, 0.0));
+    for (size_t m = 0; m < nM; m++)
+        for (size_t l = 0; l < width; l++) out[m][l] = flat[m * width + l];
+    return out;
+}
+
+static std::vector<std::vector<double> > murtyWeights(const std::vector<double>& costMatrix, size_t nL, size_t nM, size_t k,
+                                                      int cutMode, int weightMode, const char* who) {
+    const int64_t costOff = 0, probOff = 0;
+    const int32_t nr = int32_t(nL + nM), nc = int32_t(nM), nl = int32_t(nL);
+    int32_t nFound = 0;
+    std::vector<double> probs(nM * (nL + 1), 0.0);
+    pdaCheck(pda_murty_batch_host(costMatrix.data(), &costOff, &nr, &nc, 1, int32_t(k), cutMode, 42.0, 0, 0, NULL, NULL, NULL,
+                                  NULL, NULL, &nFound, weightMode, probs.data(), &probOff, &nl, pdaShimDevice()),
+             who);
+    return unflatten(probs, nM, nL + 1);
+}
+
+std::vector<std::vector<double> > assignmentProb(const std::vector<double>& costMatrix, size_t nL, size_t nM, size_t k) {
+    return murtyWeights(costMatrix, nL, nM, k, PDA_CUT_RELATIVE, PDA_WEIGHTS_GATED, "assignmentProb");
+}
+
+// upperK of bruteForceProb (assignment.cpp:28-36, 858-868).  The reference casts the Minc-type bound to
+// size_t, which is undefined once the bound exceeds 2^64; here anything at or above 20000 saturates.
+static size_t bruteForceK(const std::vector<double>& C, size_t nRows, size_t nCols) {
+    const double tau = 6.2831853071, n = double(nRows), m = double(nCols);
+    double bound = pow(tau, (m - n) / (2 * n)) * pow(n / m, m) * exp(m / (12 * n * n) - 1 / (12 * m + 1));
+    for (size_t r = 0; r < nRows; r++) {
+        double card = 1;
+        for (size_t c = 0; c < nCols; c++)
+            if (C[c * nRows + r] < std::numeric_limits<double>::infinity()) card += 1;
+        bound *= pow(tau * card, 1.0 / (2.0 * card)) * card * exp(-1 + 1.0 / (12 * card * card));
+    }
+    if (!(bound < 20000.0)) return 20000;
+    return size_t(bound) + 1;
+}
+
+std::vector<std::vector<double> > bruteForceProb(const std::vector<double>& costMatrix, size_t nL, size_t nM) {
+    const size_t k = (nM == 1) ? 1 : bruteForceK(costMatrix, nL + nM, nM);
+    return murtyWeights(costMatrix, nL, nM, k, PDA_CUT_NONE, PDA_WEIGHTS_UNGATED, "bruteForceProb");
+}
+
+std::vector<std::vector<double> > permanentProb(std::vector<double> costMatrix, size_t nL, size_t nM, int permOpt) {
+    const int64_t costOff = 0, probOff = 0;
+    const int32_t nl = int32_t(nL), nm = int32_t(nM);
+    int32_t status = 0;
+    std::vector<double> probs(nM * (nL + 1), 0.0);
+    pdaCheck(pda_permanent_prob_batch_host(costMatrix.data(), &costOff, &nl, &nm, 1, permOpt, probs.data(), &probOff, &status,
+                                           pdaShimDevice()),
+             "permanentProb");
+    if (status) {
+        if (permOpt == 1 || permOpt == 2)
+            throw std::runtime_error("Maximum matrix dimension limited to 32. Error inside permanentExactSquare().");
+        throw std::runtime_error("Unknown perm option in conditioned permanent!");
+    }
+    return unflatten(probs, nM, nL + 1);
+}
+
+std::vector<double> conditionCosts(const std::vector<double>& costs, size_t nRows, size_t nCols,
+                                   std::vector<ptrdiff_t>& rowIdxOut) {
+    const int64_t costOff = 0, rowOff = 0;
+    const int32_t nr = int32_t(nRows), nc = int32_t(nCols);
+    int32_t good = 0;
+    std::vector<double> out(costs.size() ? costs.size() : 1);
+    std::vector<int64_t> idx(nRows ? nRows : 1);
+    pdaCheck(pda_condition_costs_batch_host(costs.data(), &costOff, &nr, &nc, 1, &rowOff, out.data(), idx.data(), &good,
+                                            pdaShimDevice()),
+             "conditionCosts");
+    out.resize(size_t(good) * nCols);
+    std::vector<ptrdiff_t> rows(idx.begin(), idx.begin() + good);
+    rowIdxOut.swap(rows);
+    return out;
+}
+
+void toProbs(std::vector<double>& costMatrix) {
+    if (costMatrix.empty()) return;
+    const int64_t off = 0, len = int64_t(costMatrix.size());
+    pdaCheck(pda_to_probs_batch_host(costMatrix.data(), &off, &len, 1, pdaShimDevice()), "toProbs");
+}
+
+double conditionedPermanentRaw(const double* A, size_t rows, size_t cols, int permOpt) {
+    const int64_t off = 0;
+    const int32_t r = int32_t(rows), c = int32_t(cols);
+    int32_t status = 0;
+    double out = 0;
+    pdaCheck(pda_conditioned_permanent_batch_host(A, &off, &r, &c, 1, permOpt, &out, &status, pdaShimDevice()),
+             "conditionedPermanent");
+    if (status) {
+        if (permOpt == 1 || permOpt == 2)
+            throw std::runtime_error("Maximum matrix dimension limited to 32. Error inside permanentExactSquare().");
+        throw std::runtime_error("Unknown perm option in conditioned permanent!");
+    }
+    return out;
+}
+
+double permanentExactRaw(const double* A, size_t rows, size_t cols) {
+    const int64_t off = 0;
+    const int32_t r = int32_t(rows), c = int32_t(cols);
+    int32_t status = 0;
+    double out = 0;
+    pdaCheck(pda_permanent_batch_host(A, &off, &r, &c, 1, &out, &status, pdaShimDevice()), "permanentExact");
+    if (status) throw std::runtime_error("Maximum matrix dimension limited to 32. Error inside permanentExactSquare().");
+    return out;
+}
+
+long double permanentExactLongRaw(const double* A, size_t rows, size_t cols) { return permanentExactRaw(A, rows, cols); }
+
+std::vector<std::vector<std::vector<double> > > assignmentProbBatch(const std::vector<std::vector<double> >& costs,
+                                                                    const std::vector<size_t>& nL,
+                                                                    const std::vector<size_t>& nM, size_t k) {
+    const size_t n = costs.size();
+    std::vector<int64_t> costOff(n), probOff(n);
+    std::vector<int32_t> nr(n), nc(n), nl(n), found(n);
+    size_t nCost = 0, nProb = 0;
+    for (size_t p = 0; p < n; p++) {
+        costOff[p] = int64_t(nCost); probOff[p] = int64_t(nProb);
+        nr[p] = int32_t(nL[p] + nM[p]); nc[p] = int32_t(nM[p]); nl[p] = int32_t(nL[p]);
+        nCost += costs[p].size(); nProb += nM[p] * (nL[p] + 1);
+    }
+    std::vector<double> flat(nCost ? nCost : 1), probs(nProb ? nProb : 1);
+    for (size_t p = 0; p < n; p++) std::copy(costs[p].begin(), costs[p].end(), flat.begin() + costOff[p]);
+    if (n)
+        pdaCheck(pda_murty_batch_host(flat.data(), costOff.data(), nr.data(), nc.data(), int64_t(n), int32_t(k), PDA_CUT_RELATIVE,
+                                      42.0, 0, 0, NULL, NULL, NULL, NULL, NULL, found.data(), PDA_WEIGHTS_GATED, probs.data(),
+                                      probOff.data(), nl.data(), pdaShimDevice()),
+                 "assignmentProbBatch");
+    std::vector<std::vector<std::vector<double> > > out(n);
+    for (size_t p = 0; p < n; p++) {
+        std::vector<double> slice(probs.begin() + probOff[p], probs.begin() + probOff[p] + nM[p] * (nL[p] + 1));
+        out[p] = unflatten(slice, nM[p], nL[p] + 1);
+    }
+    return out;
+}
