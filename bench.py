@@ -261,6 +261,33 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     perm_ms = e0.elapsed_time(e1) / reps
+    # ---- config 5: ONE n = 28 permanent, Gray range split over the ranks, (hi, lo) partials all-gathered ----
+    from probabilisticsemslam_b200 import shard
+    A28 = synth.dense_square(1, 28, first=2828)[0].reshape(28, 28, order="F")
+    b28, e28 = shard.gray_range(28, world, rank)
+    rplan = dev.PermanentRangePlan(A28, b28, e28)
+    parts = torch.zeros(world * 2, dtype=torch.float64, device="cuda")
+    def perm28_step():
+        if e28 > b28:
+            rplan.run()
+        if world > 1:
+            dist.all_gather_into_tensor(parts, rplan.partial)
+        else:
+            parts.copy_(rplan.partial)
+    for _ in range(3):
+        perm28_step()
+    barrier()
+    e0.record()
+    for _ in range(10):
+        perm28_step()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / 10], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    perm28_ms = float(t.item())
+    perm28_value = shard.combine_partials(parts.cpu().numpy(), 28)
+
     fp64_peak = None
     if hasattr(lib, "pda_diag_dfma_tflops"):
         import ctypes as C
@@ -294,7 +321,10 @@ def main():
                      "note": "latency/issue-bound by construction (SURVEY.md 8d): ~16 dependent Dijkstra steps per child solve"},
         "extra": {"permanent_n24": {"gpu_ms": perm_ms, "unit": "ms", "flops": pplan.flops(),
                                     "achieved_tflops": pplan.flops() / (perm_ms * 1e-3) / 1e12,
-                                    "fp64_peak_tflops_measured": fp64_peak}},
+                                    "fp64_peak_tflops_measured": fp64_peak},
+                  "permanent_n28_sharded": {"ms": perm28_ms, "ranks": world, "value": perm28_value,
+                                            "exchange": "all_gather of 16-byte (hi, lo) partials, summed in rank order" if world > 1 else "none",
+                                            "achieved_tflops": 3.0 * 28 * 2.0 ** 27 / (perm28_ms * 1e-3) / 1e12}},
     }
     if world == 1 and not args.no_cpu:
         chk, kind, what = cpu_checker()

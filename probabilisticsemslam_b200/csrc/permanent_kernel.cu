@@ -53,24 +53,36 @@ __constant__ double kFactorial[33] = {
     8841761993739701954543616000000.0, 265252859812191058636308480000000.0,
     8222838654177922817725562880000000.0, 263130836933693530167218012160000000.0};
 
+#ifndef PERM_CHAINS
+#define PERM_CHAINS 4
+#endif
+#ifndef PERM_UNROLL
+#define PERM_UNROLL 1
+#endif
+constexpr int kPermUnroll = PERM_UNROLL;  // subsets per loop trip
+
 struct PermArgs {
     const double* mats; const int64_t* matOff; const int32_t* rows; const int32_t* cols;
     int64_t nMats;
-    // range mode (nMats == 1, square): Gray indices [begin, end), chunk length `chunk`
-    unsigned long long begin, end, chunk;
+    // range mode (nMats == 1, square): Gray indices [begin, end)
+    unsigned long long begin, end;
     int rangeMode;
+    int chunk;          // alignment of the per-thread ranges (power of two): below it every thread of a CTA flips
+                        // the same column at the same step, so the column read is a shared-memory broadcast
+    int threadsPerMat;  // 32..256 (power of two): threads of one CTA that share a matrix
+    int ctasPerMat;     // CTAs (blockIdx.x) that share a matrix
+    int maxN;           // largest dimension in the batch (sizes the shared-memory slots)
     dd* partial;        // [nMats * ctasPerMat]
-    int ctasPerMat;
 };
 
-// Walks `len` Gray indices starting at i0 (i0 % len == 0, len a power of two).
+// Walks Gray indices [i0, i1) of the NW sum: seeds x for the subset gray(i0), adds its term, then steps.
+// Correct for ANY i0, i1; the column index ctz(i) is warp-uniform whenever it is below log2(chunk).
 template <int NP>
-__device__ __forceinline__ dd walk_chunk(const double* __restrict__ sA, const double* __restrict__ sBase,
-                                         const unsigned long long i0, const unsigned long long len) {
+__device__ __forceinline__ dd walk_range(const double* __restrict__ sA, const double* __restrict__ sBase,
+                                         const unsigned long long i0, const unsigned long long i1) {
     double x[NP];
 #pragma unroll
     for (int j = 0; j < NP; ++j) x[j] = sBase[j];
-    // seed: subset = gray(i0)
     unsigned long long g = i0 ^ (i0 >> 1);
     while (g) {
         const int b = __ffsll((long long)g) - 1;
@@ -96,22 +108,28 @@ __device__ __forceinline__ dd walk_chunk(const double* __restrict__ sA, const do
         const double prod = (p0 * p1) * (p2 * p3);
         hi = (i0 & 1ULL) ? -prod : prod;
     }
-    for (unsigned long long t = 1; t < len; ++t) {
-        const unsigned long long i = i0 + t;
-        const int k = __ffsll((long long)t) - 1;  // == ctz(i): the bit in which gray(i) and gray(i-1) differ
+#pragma unroll kPermUnroll
+    for (unsigned long long i = i0 + 1; i < i1; ++i) {
+        const int k = __ffsll((long long)i) - 1;  // the bit in which gray(i) and gray(i-1) differ
         const unsigned long long gray = i ^ (i >> 1);
         const double s = ((gray >> k) & 1ULL) ? 1.0 : -1.0;
         const double* col = sA + k * NP;
-        double p0 = 1.0, p1 = 1.0, p2 = 1.0, p3 = 1.0;
+        double p[PERM_CHAINS];
+#pragma unroll
+        for (int c = 0; c < PERM_CHAINS; ++c) p[c] = 1.0;
 #pragma unroll
         for (int j = 0; j < NP; j += 2) {
             const double2 a = *reinterpret_cast<const double2*>(col + j);
             x[j] = fma(s, a.x, x[j]);
             x[j + 1] = fma(s, a.y, x[j + 1]);
-            if ((j & 3) == 0) { p0 *= x[j]; p1 *= x[j + 1]; }
-            else { p2 *= x[j]; p3 *= x[j + 1]; }
+            p[j % PERM_CHAINS] *= x[j];
+            p[(j + 1) % PERM_CHAINS] *= x[j + 1];
         }
-        const double prod = (p0 * p1) * (p2 * p3);
+#pragma unroll
+        for (int w = PERM_CHAINS / 2; w >= 1; w >>= 1)
+#pragma unroll
+            for (int c = 0; c < w; ++c) p[c] *= p[c + w];
+        const double prod = p[0];
         const double term = (i & 1ULL) ? -prod : prod;
         double s2, e;
         two_sum(hi, term, s2, e);
@@ -124,52 +142,158 @@ __device__ __forceinline__ dd walk_chunk(const double* __restrict__ sA, const do
     return r;
 }
 
+// Variant of walk_range that keeps column 0 in registers.  In Gray-code order every ODD index flips column 0,
+// so half of all steps then need no shared-memory read at all.  That matters because a broadcast LDS.128 still
+// writes 512 B into the register file: at one column read per subset the kernel is bound by that return path,
+// not by the FP64 pipe.  Requires i0 even (ranges are chunk aligned) -- the loop alternates odd / even indices.
 template <int NP>
-__global__ void __launch_bounds__(PERM_THREADS) perm_kernel(const PermArgs a) {
-    __shared__ __align__(16) double sA[NP * 32];
-    __shared__ __align__(16) double sBase[NP];
+__device__ __forceinline__ dd walk_range_c0(const double* __restrict__ sA, const double* __restrict__ sBase,
+                                            const unsigned long long i0, const unsigned long long i1) {
+    double x[NP], c0[NP];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) { x[j] = sBase[j]; c0[j] = sA[j]; }
+    unsigned long long g = i0 ^ (i0 >> 1);
+    while (g) {
+        const int b = __ffsll((long long)g) - 1;
+        g &= g - 1;
+        const double* col = sA + b * NP;
+#pragma unroll
+        for (int j = 0; j < NP; j += 2) {
+            const double2 a = *reinterpret_cast<const double2*>(col + j);
+            x[j] += a.x;
+            x[j + 1] += a.y;
+        }
+    }
+    double hi, lo = 0.0;
+    {
+        double p[PERM_CHAINS];
+#pragma unroll
+        for (int c = 0; c < PERM_CHAINS; ++c) p[c] = 1.0;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) p[j % PERM_CHAINS] *= x[j];
+#pragma unroll
+        for (int w = PERM_CHAINS / 2; w >= 1; w >>= 1)
+#pragma unroll
+            for (int c = 0; c < w; ++c) p[c] *= p[c + w];
+        hi = p[0];  // i0 is even: sign +
+    }
+    for (unsigned long long i = i0 + 1; i < i1; i += 2) {
+        {   // odd index i: column 0 from registers; gray bit 0 of an odd i is 1 ^ bit1(i)
+            const double s = ((i >> 1) & 1ULL) ? -1.0 : 1.0;
+            double p[PERM_CHAINS];
+#pragma unroll
+            for (int c = 0; c < PERM_CHAINS; ++c) p[c] = 1.0;
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+                x[j] = fma(s, c0[j], x[j]);
+                p[j % PERM_CHAINS] *= x[j];
+            }
+#pragma unroll
+            for (int w = PERM_CHAINS / 2; w >= 1; w >>= 1)
+#pragma unroll
+                for (int c = 0; c < w; ++c) p[c] *= p[c + w];
+            double s2, e;
+            two_sum(hi, -p[0], s2, e);  // odd index: sign -
+            hi = s2;
+            lo += e;
+        }
+        const unsigned long long ie = i + 1;
+        if (ie < i1) {  // even index: column ctz(ie) >= 1 from shared memory
+            const int k = __ffsll((long long)ie) - 1;
+            const double s = (((ie ^ (ie >> 1)) >> k) & 1ULL) ? 1.0 : -1.0;
+            const double* col = sA + k * NP;
+            double p[PERM_CHAINS];
+#pragma unroll
+            for (int c = 0; c < PERM_CHAINS; ++c) p[c] = 1.0;
+#pragma unroll
+            for (int j = 0; j < NP; j += 2) {
+                const double2 a = *reinterpret_cast<const double2*>(col + j);
+                x[j] = fma(s, a.x, x[j]);
+                x[j + 1] = fma(s, a.y, x[j + 1]);
+                p[j % PERM_CHAINS] *= x[j];
+                p[(j + 1) % PERM_CHAINS] *= x[j + 1];
+            }
+#pragma unroll
+            for (int w = PERM_CHAINS / 2; w >= 1; w >>= 1)
+#pragma unroll
+                for (int c = 0; c < w; ++c) p[c] *= p[c + w];
+            double s2, e;
+            two_sum(hi, p[0], s2, e);  // even index: sign +
+            hi = s2;
+            lo += e;
+        }
+    }
+    dd r;
+    r.hi = hi;
+    r.lo = lo;
+    return r;
+}
+
+#ifndef PERM_C0_MAX
+#define PERM_C0_MAX 32
+#endif
+__host__ __device__ constexpr bool perm_cache0(int np) { return np <= PERM_C0_MAX; }
+// resident CTAs per SM the register allocator must leave room for
+__host__ __device__ constexpr int perm_min_blocks(int np) {
+    return perm_cache0(np) ? (np <= 12 ? 4 : (np <= 16 ? 3 : 2)) : (np <= 16 ? 4 : (np <= 24 ? 3 : 2));
+}
+
+template <int NP>
+__global__ void __launch_bounds__(PERM_THREADS, perm_min_blocks(NP)) perm_kernel(const PermArgs a) {
+    extern __shared__ __align__(16) double smemD[];
     __shared__ dd sWarp[PERM_THREADS / 32];
-    const int m = blockIdx.y, cta = blockIdx.x, tid = threadIdx.x;
-    const int rows = a.rows[m], cols = a.cols[m];
+    const int tid = threadIdx.x, tpm = a.threadsPerMat;
+    const int slot = tid / tpm, t = tid % tpm, slots = PERM_THREADS / tpm;
+    const int64_t m = (int64_t)blockIdx.y * slots + slot;
+    const int cta = blockIdx.x;
+    const int slotDoubles = NP * a.maxN + NP;
+    double* sA = smemD + (size_t)slot * slotDoubles;
+    double* sBase = sA + NP * a.maxN;
+    const bool live = m < a.nMats;
+    const int rows = live ? a.rows[m] : 0, cols = live ? a.cols[m] : 0;
     const int n = rows > cols ? rows : cols;
-    dd acc;
-    acc.hi = 0.0;
-    acc.lo = 0.0;
-    if (n >= 1 && n <= NP && n <= PDA_MAX_PERM_DIM) {
+    const bool ok = live && n >= 1 && n <= NP && n <= PDA_MAX_PERM_DIM && n <= a.maxN;
+    if (ok) {
         const double* A = a.mats + a.matOff[m];
         // stage the matrix: ones outside the given block (nwPerm.cpp:226-228), zero rows beyond n
-        for (int e = tid; e < NP * n; e += PERM_THREADS) {
+        for (int e = t; e < NP * n; e += tpm) {
             const int j = e % NP, k = e / NP;
             double val = 0.0;
             if (j < n) val = (j < rows && k < cols) ? A[j + (size_t)k * rows] : 1.0;
             sA[e] = val;
         }
-        __syncthreads();
-        if (tid < NP) {
-            double b = 1.0;  // padded rows keep x == 1 forever
-            if (tid < n) {
-                double rs = 0.0;
-                for (int k = 0; k < n; ++k) rs += sA[tid + k * NP];
-                b = sA[tid + (n - 1) * NP] - rs / 2;  // nwPerm.cpp:289
-            }
-            sBase[tid] = b;
-        }
-        __syncthreads();
-        unsigned long long begin, end, chunk;
-        if (a.rangeMode) { begin = a.begin; end = a.end; chunk = a.chunk; }
-        else {
-            begin = 0;
-            end = 1ULL << (n - 1);
-            const unsigned long long threads = (unsigned long long)a.ctasPerMat * PERM_THREADS;
-            chunk = end / threads;
-            if (chunk < 1) chunk = 1;
-        }
-        const unsigned long long nChunks = (end - begin) / chunk;
-        const unsigned long long gid = (unsigned long long)cta * PERM_THREADS + tid;
-        const unsigned long long stride = (unsigned long long)gridDim.x * PERM_THREADS;
-        for (unsigned long long c = gid; c < nChunks; c += stride) acc = dd_add(acc, walk_chunk<NP>(sA, sBase, begin + c * chunk, chunk));
     }
-    // fixed-order reduction: lanes, then warps
+    __syncthreads();
+    if (ok && t < NP) {
+        double b = 1.0;  // padded rows keep x == 1 forever
+        if (t < n) {
+            double rs = 0.0;
+            for (int k = 0; k < n; ++k) rs += sA[t + k * NP];
+            b = sA[t + (n - 1) * NP] - rs / 2;  // nwPerm.cpp:289
+        }
+        sBase[t] = b;
+    }
+    __syncthreads();
+    dd acc;
+    acc.hi = 0.0;
+    acc.lo = 0.0;
+    if (ok) {
+        unsigned long long begin = 0, end = 1ULL << (n - 1);
+        if (a.rangeMode) { begin = a.begin; end = a.end; }
+        // contiguous, chunk-aligned share of [begin, end) for this thread
+        const unsigned long long total = end - begin, chunk = (unsigned long long)a.chunk;
+        const unsigned long long nChunks = (total + chunk - 1) / chunk;
+        const unsigned long long threads = (unsigned long long)a.ctasPerMat * tpm;
+        const unsigned long long per = (nChunks + threads - 1) / threads;
+        const unsigned long long g = (unsigned long long)cta * tpm + t;
+        unsigned long long lo = begin + g * per * chunk, hi = lo + per * chunk;
+        if (hi > end) hi = end;
+        if (g * per < nChunks && lo < hi) {
+            if (perm_cache0(NP) && (lo & 1ULL) == 0) acc = walk_range_c0<NP>(sA, sBase, lo, hi);
+            else acc = walk_range<NP>(sA, sBase, lo, hi);
+        }
+    }
+    // fixed-order reduction: lanes, then the warps that share the matrix
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
         dd other;
@@ -179,22 +303,33 @@ __global__ void __launch_bounds__(PERM_THREADS) perm_kernel(const PermArgs a) {
     }
     if ((tid & 31) == 0) sWarp[tid >> 5] = acc;
     __syncthreads();
-    if (tid == 0) {
-        dd t = sWarp[0];
-        for (int w = 1; w < PERM_THREADS / 32; ++w) t = dd_add(t, sWarp[w]);
-        a.partial[(size_t)m * a.ctasPerMat + cta] = t;
+    if (live && t == 0) {
+        const int w0 = tid >> 5, nw = tpm >> 5;
+        dd tot = sWarp[w0];
+        for (int w = 1; w < nw; ++w) tot = dd_add(tot, sWarp[w0 + w]);
+        a.partial[(size_t)m * a.ctasPerMat + cta] = tot;
     }
 }
 
-// Sums the per-CTA partials in order and applies sign, factor 2 and the rectangular scale.
+// One warp per matrix: sums the per-CTA partials (lane-strided, then a fixed shuffle tree -- the order depends
+// only on ctasPerMat, so results are reproducible) and applies sign, factor 2 and the rectangular scale.
 __global__ void perm_finalize_kernel(const PermArgs a, double* __restrict__ out, int32_t* __restrict__ status,
                                      double* __restrict__ rangePartial) {
-    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (m >= a.nMats) return;
     dd t;
     t.hi = 0.0;
     t.lo = 0.0;
-    for (int c = 0; c < a.ctasPerMat; ++c) t = dd_add(t, a.partial[(size_t)m * a.ctasPerMat + c]);
+    for (int c = lane; c < a.ctasPerMat; c += 32) t = dd_add(t, a.partial[(size_t)m * a.ctasPerMat + c]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        dd other;
+        other.hi = __shfl_down_sync(FULL, t.hi, o);
+        other.lo = __shfl_down_sync(FULL, t.lo, o);
+        t = dd_add(t, other);
+    }
+    if (lane != 0) return;
     if (a.rangeMode) {
         rangePartial[0] = t.hi;
         rangePartial[1] = t.lo;
@@ -211,34 +346,59 @@ __global__ void perm_finalize_kernel(const PermArgs a, double* __restrict__ out,
 }
 
 template <int NP>
-int launch_np(const PermArgs& a, int gridX, cudaStream_t stream) {
-    dim3 grid((unsigned)gridX, (unsigned)a.nMats);
-    perm_kernel<NP><<<grid, PERM_THREADS, 0, stream>>>(a);
+int launch_np(const PermArgs& a, cudaStream_t stream) {
+    const int slots = PERM_THREADS / a.threadsPerMat;
+    const size_t smem = (size_t)slots * (NP * a.maxN + NP) * sizeof(double);
+    PDA_CUDA_TRY(cudaFuncSetAttribute(perm_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)a.ctasPerMat, (unsigned)((a.nMats + slots - 1) / slots));
+    perm_kernel<NP><<<grid, PERM_THREADS, smem, stream>>>(a);
     PDA_CUDA_TRY(cudaGetLastError());
     return PDA_OK;
 }
 
-int dispatch(const PermArgs& a, int maxDim, int gridX, cudaStream_t stream) {
-    const int np = std::max(2, (maxDim + 1) / 2 * 2);
+int dispatch(const PermArgs& a, cudaStream_t stream) {
+    const int np = std::max(2, (a.maxN + 1) / 2 * 2);
     switch (np) {
-#define PDA_CASE(N) case N: return launch_np<N>(a, gridX, stream);
+#define PDA_CASE(N) case N: return launch_np<N>(a, stream);
         PDA_CASE(2) PDA_CASE(4) PDA_CASE(6) PDA_CASE(8) PDA_CASE(10) PDA_CASE(12) PDA_CASE(14) PDA_CASE(16)
         PDA_CASE(18) PDA_CASE(20) PDA_CASE(22) PDA_CASE(24) PDA_CASE(26) PDA_CASE(28) PDA_CASE(30) PDA_CASE(32)
 #undef PDA_CASE
     }
-    return fail(PDA_ERR_UNSUPPORTED, "permanent: dimension %d above %d", maxDim, PDA_MAX_PERM_DIM);
+    return fail(PDA_ERR_UNSUPPORTED, "permanent: dimension %d above %d", a.maxN, PDA_MAX_PERM_DIM);
 }
-
-int pow2_floor(long long x) { int p = 1; while ((long long)p * 2 <= x) p *= 2; return p; }
 
 }  // namespace
 
-// CTAs per matrix: enough CTAs to fill the chip, but at least 64 subsets per thread.
-static int ctas_per_matrix(int64_t nMats, int maxDim, int smCount) {
-    const long long subsets = 1LL << std::max(0, std::min(maxDim, PDA_MAX_PERM_DIM) - 1);
-    long long byWork = std::max(1LL, subsets / ((long long)PERM_THREADS * 64));
-    long long byChip = std::max<long long>(1, (2LL * smCount + nMats - 1) / nMats);
-    return pow2_floor(std::max(1LL, std::min(byWork, std::min(byChip, 1024LL))));
+// Launch shape for a batch whose largest dimension is maxDim: threads that share a matrix (small matrices get
+// one warp each, eight to a CTA), CTAs per matrix (a few large matrices are spread over the whole chip, in
+// multiples that fill 2 CTAs per SM evenly), and the alignment of the per-thread index ranges.
+struct PermShape { int threadsPerMat, ctasPerMat, chunk; };
+static PermShape perm_shape(int64_t nMats, int maxDim, int smCount, unsigned long long rangeLen) {
+    const int n = std::max(1, std::min(maxDim, PDA_MAX_PERM_DIM));
+    const unsigned long long steps = rangeLen ? rangeLen : (1ULL << (n - 1));
+    PermShape sh;
+    int tpm = 32;
+    while (tpm < PERM_THREADS && (unsigned long long)tpm * 64 < steps) tpm *= 2;
+    sh.threadsPerMat = tpm;
+    const long long slots = PERM_THREADS / tpm;
+    const long long ctasForBatch = (nMats + slots - 1) / slots;
+    long long cpm = 1;
+    if (tpm == PERM_THREADS) {
+        // few large matrices: spread each over the chip.  Prefer a CTA count that fills every SM evenly
+        // (a multiple of the SM count) while leaving >= 96 subsets per thread; otherwise as many as the work allows.
+        const int np = std::max(2, (n + 1) / 2 * 2);
+        const long long byWork = (long long)std::max<unsigned long long>(1, steps / ((unsigned long long)PERM_THREADS * 96));
+        const long long perSmMax = perm_min_blocks(np);
+        long long total = std::min(byWork * ctasForBatch, perSmMax * smCount);           // CTAs for the whole batch
+        if (total >= smCount) total = total / smCount * smCount;
+        cpm = std::max(1LL, std::min(total / ctasForBatch, 4096LL));
+    }
+    sh.ctasPerMat = (int)cpm;
+    const unsigned long long perThread = std::max<unsigned long long>(1, steps / ((unsigned long long)cpm * tpm));
+    int chunk = 1;
+    while (chunk < 32 && (unsigned long long)chunk * 2 * 6 <= perThread) chunk *= 2;  // >= 6 chunks per thread keeps the shares even
+    sh.chunk = chunk;
+    return sh;
 }
 
 int launch_permanent_batch(const double* mats, const int64_t* matOff, const int32_t* rows, const int32_t* cols,
@@ -246,22 +406,24 @@ int launch_permanent_batch(const double* mats, const int64_t* matOff, const int3
                            int64_t workspaceBytes, cudaStream_t stream) {
     DeviceInfo dev;
     PDA_TRY(current_device_info(&dev));
-    const int effDim = std::min<int>(maxDim, PDA_MAX_PERM_DIM);
-    int cpm = ctas_per_matrix(nMats, effDim, dev.smCount);
-    while (cpm > 1 && (int64_t)cpm * nMats * (int64_t)sizeof(dd) > workspaceBytes) cpm >>= 1;
-    if ((int64_t)cpm * nMats * (int64_t)sizeof(dd) > workspaceBytes)
+    const int effDim = std::max(1, std::min<int>(maxDim, PDA_MAX_PERM_DIM));
+    PermShape sh = perm_shape(nMats, effDim, dev.smCount, 0);
+    while (sh.ctasPerMat > 1 && (int64_t)sh.ctasPerMat * nMats * (int64_t)sizeof(dd) > workspaceBytes) sh.ctasPerMat >>= 1;
+    if ((int64_t)sh.ctasPerMat * nMats * (int64_t)sizeof(dd) > workspaceBytes)
         return fail(PDA_ERR_WORKSPACE, "permanent: workspace of %lld B too small (need %lld)", (long long)workspaceBytes,
                     (long long)(nMats * (int64_t)sizeof(dd)));
-    PermArgs a = {mats, matOff, rows, cols, nMats, 0, 0, 0, 0, reinterpret_cast<dd*>(workspace), cpm};
+    PermArgs a = {mats, matOff, rows, cols, nMats, 0, 0, 0, sh.chunk, sh.threadsPerMat, sh.ctasPerMat, effDim,
+                  reinterpret_cast<dd*>(workspace)};
     // blockIdx.y is limited to 65535: slice the batch
-    for (int64_t m0 = 0; m0 < nMats; m0 += 65535) {
+    const int64_t slots = PERM_THREADS / sh.threadsPerMat, perLaunch = 65535 * slots;
+    for (int64_t m0 = 0; m0 < nMats; m0 += perLaunch) {
         PermArgs s = a;
         s.matOff = matOff + m0; s.rows = rows + m0; s.cols = cols + m0;
-        s.nMats = std::min<int64_t>(65535, nMats - m0);
-        s.partial = a.partial + m0 * cpm;
-        PDA_TRY(dispatch(s, std::max(effDim, 1), cpm, stream));
+        s.nMats = std::min<int64_t>(perLaunch, nMats - m0);
+        s.partial = a.partial + m0 * sh.ctasPerMat;
+        PDA_TRY(dispatch(s, stream));
     }
-    perm_finalize_kernel<<<(unsigned)((nMats + 127) / 128), 128, 0, stream>>>(a, out, status, nullptr);
+    perm_finalize_kernel<<<(unsigned)((nMats + 3) / 4), 128, 0, stream>>>(a, out, status, nullptr);
     PDA_CUDA_TRY(cudaGetLastError());
     return PDA_OK;
 }
@@ -270,18 +432,13 @@ int launch_permanent_range(const double* A, int32_t n, uint64_t begin, uint64_t 
                            void* workspace, int64_t workspaceBytes, cudaStream_t stream) {
     DeviceInfo dev;
     PDA_TRY(current_device_info(&dev));
-    // chunk: largest power of two dividing both ends, capped so that there are enough chunks to fill the chip
-    const unsigned long long total = end - begin;
-    unsigned long long align = (begin | end) ? ((begin | end) & (~(begin | end) + 1ULL)) : (1ULL << 62);
-    unsigned long long chunk = 1;
-    const unsigned long long wantThreads = 2ULL * dev.smCount * PERM_THREADS;
-    while (chunk * 2 <= align && total / (chunk * 2) >= wantThreads) chunk *= 2;
-    while (chunk * 2 <= align && chunk < 64 && total / (chunk * 2) >= 1) chunk *= 2;
-    const unsigned long long nChunks = total / chunk;
-    int gridX = (int)std::min<unsigned long long>((nChunks + PERM_THREADS - 1) / PERM_THREADS, 8ULL * dev.smCount);
-    gridX = std::max(gridX, 1);
-    if ((int64_t)gridX * (int64_t)sizeof(dd) + 64 > workspaceBytes)
-        return fail(PDA_ERR_WORKSPACE, "permanent_range: workspace too small");
+    PermShape sh = perm_shape(1, n, dev.smCount, end - begin);
+    // keep the ranges uniform inside a warp: the chunk must divide `begin`
+    while (sh.chunk > 1 && (begin % (unsigned long long)sh.chunk) != 0) sh.chunk >>= 1;
+    if ((int64_t)sh.ctasPerMat * (int64_t)sizeof(dd) + 64 > workspaceBytes) {
+        sh.ctasPerMat = (int)std::max<int64_t>(1, (workspaceBytes - 64) / (int64_t)sizeof(dd));
+        if (workspaceBytes < 64 + (int64_t)sizeof(dd)) return fail(PDA_ERR_WORKSPACE, "permanent_range: workspace too small");
+    }
     // the single matrix is described by tiny device-side descriptors at the head of the workspace
     unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
     int64_t* dOff = reinterpret_cast<int64_t*>(ws);
@@ -289,8 +446,9 @@ int launch_permanent_range(const double* A, int32_t n, uint64_t begin, uint64_t 
     int32_t* dCols = reinterpret_cast<int32_t*>(ws + 12);
     struct { int64_t off; int32_t r, c; } desc = {0, n, n};
     PDA_CUDA_TRY(cudaMemcpyAsync(ws, &desc, 16, cudaMemcpyHostToDevice, stream));
-    PermArgs a = {A, dOff, dRows, dCols, 1, begin, end, chunk, 1, reinterpret_cast<dd*>(ws + 64), gridX};
-    PDA_TRY(dispatch(a, n, gridX, stream));
+    PermArgs a = {A, dOff, dRows, dCols, 1, begin, end, 1, sh.chunk, sh.threadsPerMat, sh.ctasPerMat, n,
+                  reinterpret_cast<dd*>(ws + 64)};
+    PDA_TRY(dispatch(a, stream));
     perm_finalize_kernel<<<1, 32, 0, stream>>>(a, nullptr, nullptr, partial);
     PDA_CUDA_TRY(cudaGetLastError());
     return PDA_OK;
@@ -303,7 +461,7 @@ using namespace pda;
 extern "C" {
 
 int64_t pda_permanent_workspace_bytes(int64_t nMats) {
-    return 64 + 16 * (std::max<int64_t>(nMats, 1) + 1024);
+    return 64 + 16 * (std::max<int64_t>(nMats, 1) + 8192);
 }
 
 int pda_permanent_batch(const double* mats, const int64_t* matOff, const int32_t* rows, const int32_t* cols,
@@ -334,8 +492,7 @@ int pda_permanent_batch_host(const double* mats, const int64_t* matOff, const in
     DeviceInfo dev;
     PDA_TRY(current_device_info(&dev));
     const size_t n = (size_t)nMats;
-    const int cpm = ctas_per_matrix(nMats, std::min(maxDim, PDA_MAX_PERM_DIM), dev.smCount);
-    const size_t wsBytes = n * cpm * sizeof(double) * 2;
+    const size_t wsBytes = (size_t)pda_permanent_workspace_bytes(nMats);
     Stage st(device);
     const size_t oM = st.reserve(nEl * 8), oOff = st.reserve(n * 8), oR = st.reserve(n * 4), oC = st.reserve(n * 4);
     const size_t oOut = st.reserve(n * 8), oSt = st.reserve(n * 4), oWs = st.reserve(wsBytes);
@@ -373,7 +530,7 @@ int pda_permanent_range_host(const double* A, int32_t n, uint64_t begin, uint64_
     PDA_TRY(check_device(device));
     DeviceInfo dev;
     PDA_TRY(current_device_info(&dev));
-    const size_t wsBytes = 64 + (size_t)8 * dev.smCount * 16;
+    const size_t wsBytes = 64 + (size_t)16 * 8192;
     Stage st(device);
     const size_t oA = st.reserve((size_t)n * n * 8), oP = st.reserve(16), oWs = st.reserve(wsBytes);
     PDA_TRY(st.commit());
