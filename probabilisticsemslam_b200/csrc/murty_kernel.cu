@@ -113,6 +113,80 @@ __device__ __forceinline__ void relax(const double* __restrict__ Ccol, const int
     }
 }
 
+constexpr int NAN_HI = 0x7ff80000;  // high word of the NaN that marks a scanned row's candidate
+
+// Fast-forward over the reference's no-op hops.
+//
+// Most Dijkstra steps of a child solve (93 % on the benchmark shapes) go through rows that are paired with
+// zero-cost PADDING columns and change nothing: scanning such a column p from row r offers every other row
+// t = (cand[r] - u[p]) - v[row], which is not below what the row already holds, so the reference merely retires
+// r and moves to the next-closest row.  This routine proves that for a whole run of such rows at once and
+// retires them together, with results bit-identical to stepping through them:
+//   stopper  = the closest live row that is NOT paired with a padding column (a free row -- the sink -- or a row
+//              whose column has real costs); key order is (cand, row), the reference's first-minimum order
+//   F        = live rows paired with padding columns that come before the stopper in that order
+//   W        = min over F of fl(cand[r] - u[col(r)])   (what each of those hops would offer, before the row dual)
+//   test     : fl(W - v[row]) >= cand[row] for EVERY live row.  Rounding is monotone, so fl(W - v) is the smallest
+//              offer any hop of F could make to that row; if even that does not beat its candidate, no hop of F
+//              updates anything, in any order (a sufficient condition -- it also covers offers from hops that
+//              come after the row, which the reference never makes).
+// If the test passes every row of F is scanned at its current candidate (parked in sm.spc), predecessors stay as
+// they are, and the stopper is the next row to scan: (closest, delta) are returned so the caller skips its own
+// arg-min.  If it fails nothing is changed and the caller steps normally.  Returns 0 = not applied,
+// 1 = applied, 2 = applied and nothing finite is left (infeasible).
+template <int R>
+__device__ __forceinline__ int fast_forward(const int numColReal, const WarpSmem& sm, const Node<R>& nd,
+                                            const double (&vEff)[R], const double (&uRow)[R], double (&cand)[R],
+                                            int& closest, double& delta, const int lane) {
+    // the stopper
+    double sb = CUDART_INF;
+    int sbs = 0;
+#pragma unroll
+    for (int s = 0; s < R; ++s)
+        if (nd.c4r[s] < numColReal && cand[s] < sb) { sb = cand[s]; sbs = s; }
+    unsigned khi, klo;
+    to_key(sb, khi, klo);
+    const unsigned mhi = __reduce_min_sync(FULL, khi);
+    const unsigned mlo = __reduce_min_sync(FULL, (khi == mhi) ? klo : 0xffffffffu);
+    const bool win = (khi == mhi) && (klo == mlo);
+    const int rT = (int)__reduce_min_sync(FULL, win ? (unsigned)(lane + 32 * sbs) : 0xffffu);
+    const double kT = from_key(mhi, mlo);
+    // F and what its hops would offer
+    unsigned inF = 0u;
+    double wmin = CUDART_INF;
+    int nF = 0;
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+        const bool f = nd.c4r[s] >= numColReal && cand[s] < CUDART_INF &&
+                       (cand[s] < kT || (cand[s] == kT && lane + 32 * s < rT));
+        if (f) {
+            inF |= 1u << s;
+            const double w = cand[s] - uRow[s];
+            wmin = (w < wmin) ? w : wmin;
+        }
+        nF += __popc(__ballot_sync(FULL, f));
+    }
+    if (nF < 2) return 0;
+    to_key(wmin, khi, klo);
+    const unsigned whi = __reduce_min_sync(FULL, khi);
+    const unsigned wlo = __reduce_min_sync(FULL, (khi == whi) ? klo : 0xffffffffu);
+    const double W = from_key(whi, wlo);
+    bool beats = false;
+#pragma unroll
+    for (int s = 0; s < R; ++s) beats = beats || ((W - vEff[s]) < cand[s]);
+    if (__any_sync(FULL, beats)) return 0;
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+        if ((inF >> s) & 1u) {
+            sm.spc[lane + 32 * s] = cand[s];
+            cand[s] = __hiloint2double(NAN_HI, __double2loint(cand[s]));
+        }
+    }
+    closest = rT;
+    delta = kT;
+    return (mhi >= KEY_INF_HI) ? 2 : 1;
+}
+
 // One shortest augmenting path from `startCol` over the rows flagged in scanBits
 // (bit s = row lane+32s), then the dual update and the flip along the path.
 //   shortestPathCPP.cpp:168-226 / 297-356 (scan), :92-106 (duals), :108-116 (flip).
@@ -124,8 +198,6 @@ __device__ __forceinline__ void relax(const double* __restrict__ Ccol, const int
 // its cand poisoned to NaN (one high-word write): `t < NaN` is false, so it never relaxes again, the
 // arg-min skips it, and "scanned" can be read back from it afterwards.  The cost at which a row was
 // scanned (== delta at that moment) is parked in sm.spc by lane 0, where the dual update reads it.
-constexpr int NAN_HI = 0x7ff80000;
-
 template <int R>
 __device__ __forceinline__ bool augment_from(const int startCol, const int numColReal, const int ld,
                                              const WarpSmem& sm, Node<R>& nd, const unsigned scanBits,
@@ -148,20 +220,31 @@ __device__ __forceinline__ bool augment_from(const int startCol, const int numCo
         if (cur < numColReal) relax<R, true>(sm.C + cur * ld, ld, delta, ucur, vHop, cur, cand, pred, lane);
         else relax<R, false>(nullptr, ld, delta, ucur, vHop, cur, cand, pred, lane);
     }
-    for (;;) {
-        // lane-local first minimum (lower slot = lower row wins ties; NaN = already scanned), then the warp arg-min
-        double best = cand[0];
-        int bs = 0;
+    // u of the column each owned row is paired with (only rows paired with padding columns use it)
+    double uRow[R];
 #pragma unroll
-        for (int s = 1; s < R; ++s) if (cand[s] < best || best != best) { best = cand[s]; bs = s; }
-        unsigned khi, klo;
-        to_key(best, khi, klo);
-        const unsigned mhi = __reduce_min_sync(FULL, khi);
-        if (mhi >= KEY_INF_HI) return true;  // minVal == +inf (:197, :327): nothing finite is left
-        const unsigned mlo = __reduce_min_sync(FULL, (khi == mhi) ? klo : 0xffffffffu);
-        const bool win = (khi == mhi) && (klo == mlo);
-        const int closest = (int)__reduce_min_sync(FULL, win ? (unsigned)(lane + 32 * bs) : 0xffffu);
-        delta = from_key(mhi, mlo);
+    for (int s = 0; s < R; ++s) uRow[s] = (nd.c4r[s] >= 0) ? sm.u[nd.c4r[s]] : 0.0;
+    bool padPrev = cur >= numColReal;  // the last relaxation came from a padding column
+    for (;;) {
+        int closest = 0;
+        int ff = 0;
+        if (padPrev) ff = fast_forward<R>(numColReal, sm, nd, vEff, uRow, cand, closest, delta, lane);
+        if (ff == 2) return true;
+        if (ff == 0) {
+            // lane-local first minimum (lower slot = lower row wins ties; NaN = already scanned), then the warp arg-min
+            double best = cand[0];
+            int bs = 0;
+#pragma unroll
+            for (int s = 1; s < R; ++s) if (cand[s] < best || best != best) { best = cand[s]; bs = s; }
+            unsigned khi, klo;
+            to_key(best, khi, klo);
+            const unsigned mhi = __reduce_min_sync(FULL, khi);
+            if (mhi >= KEY_INF_HI) return true;  // minVal == +inf (:197, :327): nothing finite is left
+            const unsigned mlo = __reduce_min_sync(FULL, (khi == mhi) ? klo : 0xffffffffu);
+            const bool win = (khi == mhi) && (klo == mlo);
+            closest = (int)__reduce_min_sync(FULL, win ? (unsigned)(lane + 32 * bs) : 0xffffu);
+            delta = from_key(mhi, mlo);
+        }
         if (lane == 0) sm.spc[closest] = delta;
 #pragma unroll
         for (int s = 0; s < R; ++s)
@@ -169,9 +252,10 @@ __device__ __forceinline__ bool augment_from(const int startCol, const int numCo
         const unsigned next = sm.c4r[closest];
         if (next == 0xffffu) { sink = closest; break; }
         cur = (int)next;
+        padPrev = cur >= numColReal;
         const double ucur = sm.u[cur];
-        if (cur < numColReal) relax<R, true>(sm.C + cur * ld, ld, delta, ucur, vEff, cur, cand, pred, lane);
-        else relax<R, false>(nullptr, ld, delta, ucur, vEff, cur, cand, pred, lane);
+        if (padPrev) relax<R, false>(nullptr, ld, delta, ucur, vEff, cur, cand, pred, lane);
+        else relax<R, true>(sm.C + cur * ld, ld, delta, ucur, vEff, cur, cand, pred, lane);
     }
 
     // duals, using row4col as it was before the flip (:92-106).  A column other than startCol was scanned
