@@ -311,30 +311,46 @@ __device__ __forceinline__ double path_gain(const WarpSmem& sm, const int ld, co
     return g;
 }
 
-// ---- heap in the warp's arena: lane 0 only ---------------------------------------------------------
-__device__ __forceinline__ void heap_sift_up(HeapEntry* h, int hole, const HeapEntry val) {
-    int parent = (hole - 1) / 2;
-    while (hole > 0 && h[parent].gain > val.gain) {
-        h[hole] = h[parent];
-        hole = parent;
-        parent = (hole - 1) / 2;
+// ---- the heap: lane 0 only ----------------------------------------------------------------------------
+// Entries are 16 bytes and move as one 128-bit access.  The first `topCap` entries (the top levels, which every
+// pop walks through) live in the warp's shared memory, the rest in its global arena: a pop's sift-down is a chain
+// of dependent loads, and this turns most of its ~10 L2 round trips into shared-memory reads.
+struct Heap {
+    HeapEntry* top;   // shared memory, entries [0, topCap)
+    HeapEntry* deep;  // global arena, entry i at deep[i] (slots below topCap unused)
+    int topCap;
+    __device__ __forceinline__ HeapEntry get(int i) const { return (i < topCap) ? top[i] : deep[i]; }
+    __device__ __forceinline__ void put(int i, const HeapEntry& e) const {
+        if (i < topCap) top[i] = e; else deep[i] = e;
     }
-    h[hole] = val;
+};
+
+__device__ __forceinline__ void heap_sift_up(const Heap& h, int hole, const HeapEntry val) {
+    while (hole > 0) {
+        const int parent = (hole - 1) / 2;
+        const HeapEntry par = h.get(parent);
+        if (!(par.gain > val.gain)) break;
+        h.put(hole, par);
+        hole = parent;
+    }
+    h.put(hole, val);
 }
-__device__ __forceinline__ void heap_pop(HeapEntry* h, const int lenBefore) {
+__device__ __forceinline__ void heap_pop(const Heap& h, const int lenBefore) {
     if (lenBefore > 1) {
         const int len = lenBefore - 1;
-        const HeapEntry val = h[len];
+        const HeapEntry val = h.get(len);
         int hole = 0, child = 0;
         while (child < (len - 1) / 2) {
             child = 2 * (child + 1);
-            if (h[child].gain > h[child - 1].gain) child--;  // right child wins an exact tie
-            h[hole] = h[child];
+            const HeapEntry right = h.get(child), left = h.get(child - 1);  // both children in one round trip
+            const bool takeLeft = right.gain > left.gain;                     // right child wins an exact tie
+            if (takeLeft) child--;
+            h.put(hole, takeLeft ? left : right);
             hole = child;
         }
         if ((len & 1) == 0 && child == (len - 2) / 2) {
             child = 2 * (child + 1);
-            h[hole] = h[child - 1];
+            h.put(hole, h.get(child - 1));
             hole = child - 1;
         }
         heap_sift_up(h, hole, val);
@@ -456,7 +472,7 @@ __device__ __forceinline__ void add_weight(const MurtyArgs& a, const WarpSmem& s
 }
 
 template <int R>
-__device__ void solve_problem(const MurtyArgs& a, const long long p, const WarpSmem& sm, HeapEntry* heap,
+__device__ void solve_problem(const MurtyArgs& a, const long long p, const WarpSmem& sm, const Heap& heap,
                               unsigned char* nodes, const int lane) {
     const int n = a.numRow[p], nc = a.numCol[p];
     const int D = a.geo.nodeDim;
@@ -583,7 +599,7 @@ __device__ void solve_problem(const MurtyArgs& a, const long long p, const WarpS
         if (heapLen == 0) break;
 
         // ---- the new top is hypothesis number `sweep` (:703-719) ---------------------------
-        HeapEntry top = heap[0];
+        const HeapEntry top = heap.get(0);
         gain = top.gain;
         node_load<R>(nodes + (size_t)top.node * a.geo.nodeStride, D, n, nd, forb, activeCol, lane);
         double gainOut;
@@ -630,7 +646,10 @@ __global__ void __launch_bounds__(128, PDA_MURTY_MINB) murty_kernel(const MurtyA
     if (gw >= a.nWarps) return;
     const WarpSmem sm = carve(smemRaw + (size_t)warp * a.geo.smemPerWarp, a.geo);
     unsigned char* arena = a.arena + (size_t)gw * a.geo.arenaStride;
-    HeapEntry* heap = reinterpret_cast<HeapEntry*>(arena);
+    Heap heap;
+    heap.deep = reinterpret_cast<HeapEntry*>(arena);
+    heap.top = reinterpret_cast<HeapEntry*>(smemRaw + (size_t)warp * a.geo.smemPerWarp + a.geo.heapTopOff);
+    heap.topCap = a.geo.heapTopCap;
     unsigned char* nodes = arena + a.geo.heapBytes;
     for (;;) {
         unsigned long long p = 0;
@@ -716,7 +735,15 @@ int murty_geometry(int32_t k, int32_t maxNumRow, int32_t maxNumCol, bool weights
     g->arenaStride = (g->heapBytes + nodes * g->nodeStride + 255) / 256 * 256;
     g->cCap = round_up(maxNumRow * maxNumCol, 2);
     g->pCap = weights ? round_up(maxNumCol * maxNumRow, 2) : 0;
-    g->smemPerWarp = round_up(8 * (g->cCap + g->pCap + 2 * D) + 3 * 2 * D, 16);
+    const int baseSmem = round_up(8 * (g->cCap + g->pCap + 2 * D) + 3 * 2 * D, 16);
+    // leftover shared memory (at the 24 warps per SM the register budget allows) holds the top of the heap
+    const int budget = (227 * 1024 - 6 * 1024) / 24;
+    int topCap = budget > baseSmem ? (budget - baseSmem) / (int)sizeof(HeapEntry) : 0;
+    if (topCap > g->maxNodes) topCap = g->maxNodes;
+    if (topCap < 3) topCap = 0;
+    g->heapTopOff = baseSmem;
+    g->heapTopCap = topCap;
+    g->smemPerWarp = baseSmem + topCap * (int)sizeof(HeapEntry);
     if (g->smemPerWarp > dev.maxSmemOptin)
         return fail(PDA_ERR_UNSUPPORTED, "murty: a %d x %d problem needs %d B of shared memory per warp (limit %d)",
                     maxNumRow, maxNumCol, g->smemPerWarp, dev.maxSmemOptin);

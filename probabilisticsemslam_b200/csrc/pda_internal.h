@@ -34,6 +34,8 @@ struct MurtyGeometry {
     int64_t heapBytes;  // bytes of the heap region at the head of each arena
     int64_t arenaStride;
     int smemPerWarp;
+    int heapTopOff;     // byte offset of the shared-memory heap top inside a warp's shared region
+    int heapTopCap;     // heap entries kept in shared memory
     int cCap;           // doubles reserved for the cost matrix per warp
     int pCap;           // doubles reserved for the weight accumulators per warp
     int warpsPerCta;

@@ -128,6 +128,27 @@ def test_large_dimension_vs_oracle(gpu_api, oracle):
     _compare_batch(gpu_api, oracle, pb, 40)
 
 
+def test_rounding_stress_vs_oracle(gpu_api, oracle):
+    """Costs spread over twelve decades and costs that are exact multiples of 2^-20: the row scan's fast-forward
+    over no-op padding hops must reproduce every last-bit effect of stepping through them one by one."""
+    rng = np.random.default_rng(2024)
+    mats = []
+    for i in range(120):
+        nL, nM = int(rng.integers(5, 40)), int(rng.integers(2, 9))
+        C = np.full((nL + nM, nM), np.inf)
+        if i % 3 == 0:
+            C[:nL, :] = 10.0 ** rng.uniform(-6, 6, size=(nL, nM))
+        elif i % 3 == 1:
+            C[:nL, :] = np.round(rng.uniform(0, 30, size=(nL, nM)) * 2 ** 20) / 2 ** 20
+        else:
+            C[:nL, :] = rng.uniform(0, 40, size=(nL, nM)) * (rng.random((nL, nM)) < 0.6) + 1e-9 * rng.random((nL, nM))
+        C[nL + np.arange(nM), np.arange(nM)] = 10.0 if i % 2 else 1e-3
+        mats.append(C)
+    pb = synth.pack(mats, [m.shape[0] - m.shape[1] for m in mats])
+    _compare_batch(gpu_api, oracle, pb, 150)
+    _compare_batch(gpu_api, oracle, pb, 150, cut_mode=gpu_api.CUT_NONE)
+
+
 def test_maximize_vs_oracle(gpu_api, oracle):
     mats = []
     for p in range(20):
