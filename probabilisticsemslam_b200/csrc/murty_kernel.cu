@@ -404,6 +404,7 @@ __device__ __forceinline__ void node_load(const unsigned char* base, const int D
 
 template <int R>
 __device__ __forceinline__ void publish_cols(const WarpSmem& sm, const Node<R>& nd, const int lane) {
+    __syncwarp();  // earlier readers of the mirrors (gain, new row) are done before they are overwritten
 #pragma unroll
     for (int s = 0; s < R; ++s) {
         sm.u[lane + 32 * s] = nd.u[s];
@@ -600,6 +601,7 @@ __device__ void solve_problem(const MurtyArgs& a, const long long p, const WarpS
 
         // ---- the new top is hypothesis number `sweep` (:703-719) ---------------------------
         const HeapEntry top = heap.get(0);
+        __syncwarp();  // every lane has read the top before lane 0 starts the next pop
         gain = top.gain;
         node_load<R>(nodes + (size_t)top.node * a.geo.nodeStride, D, n, nd, forb, activeCol, lane);
         double gainOut;
