@@ -46,6 +46,17 @@ K_BEST = 200
 WORKLOAD = "configs[1]: 100k KITTI-shaped problems (3-8 detections x 30 landmarks + missed-detection slack), k=200, G1 seed 20260217"
 
 
+def measured_traffic(n, k):
+    """DRAM bytes of one launch of the headline kernel from the committed ncu capture (profiles/traffic.json),
+    when it was taken at this problem count; None otherwise."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)["murty_kernel<2>"]
+        return t["dram_bytes"] if (t["problems"] == n and t["k"] == k) else None
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -316,9 +327,11 @@ def main():
                 "matches_device_run": e2e_matches},
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                     "traffic": None, "peak_source": pk_kind, "kernel": "murty_kernel<2>", "kernel_ms": kernel_ms,
+                     "traffic": measured_traffic(n, k), "peak_source": pk_kind, "kernel": "murty_kernel<2>", "kernel_ms": kernel_ms,
                      "algorithmic_bytes_per_launch": alg_bytes,
-                     "note": "latency/issue-bound by construction (SURVEY.md 8d): ~16 dependent Dijkstra steps per child solve"},
+                     "note": "issue/ALU-pipe bound by construction (SURVEY.md 8d), not HBM bound. traffic (ncu, profiles/) exceeds the "
+                             "algorithmic bytes by the node arena: every Murty child (736 B of duals + pairing) is spilled once and half are "
+                             "read back (~445 KB per problem); inputs are read once"},
         "extra": {"permanent_n24": {"gpu_ms": perm_ms, "unit": "ms", "flops": pplan.flops(),
                                     "achieved_tflops": pplan.flops() / (perm_ms * 1e-3) / 1e12,
                                     "fp64_peak_tflops_measured": fp64_peak},
