@@ -31,6 +31,13 @@ std::vector<double> conditionCosts(const std::vector<double>& costs, size_t nRow
 
 void toProbs(std::vector<double>& costMatrix);
 
+/* The body of getAssignmentProbs (assignment.cpp:57-74) from the cost matrix on: conditionCosts, then
+ * assignmentProb(k) or (usePerm) permanentProb(.., 1) on the conditioned problem, then the weights scattered back to
+ * the original landmark indices.  costMatrix is what computeQuadricCostMatrix returns ((nL+nM) x nM, column-major).
+ * In the reference's getAssignmentProbs, replace lines :57-74 by a call to this. */
+std::vector<std::vector<double> > getAssignmentProbsFromCosts(const std::vector<double>& costMatrix, size_t nL, size_t nM,
+                                                              size_t k, bool usePerm);
+
 /* raw form of conditionedPermanent: A is rows x cols, column-major */
 double conditionedPermanentRaw(const double* A, size_t rows, size_t cols, int permOpt);
 #ifdef PDA_HAVE_EIGEN

@@ -127,6 +127,24 @@ int pda_to_probs_batch(double* values, const int64_t* off, const int64_t* len, i
 int pda_to_probs_batch_host(double* values, const int64_t* off, const int64_t* len, int64_t nVectors, int32_t device);
 
 /* ------------------------------------------------------------------------------------------
+ * The numeric body of getAssignmentProbs (assignment.cpp:57-74) with usePerm == 0, fused on the device:
+ * conditionCosts -> assignmentProb(k) on the conditioned problem -> weights scattered back to the original
+ * landmark indices through rowIdx.  In: the raw (nL+nM) x nM cost matrices (what computeQuadricCostMatrix,
+ * assignment.cpp:705-722, produces).  Out: probs[p] = nM x (nL+1) row-major at probOff[p]; nL == 0 gives {1}
+ * per detection (:51-53).  rowOff = prefix sums of (nL+nM); the total* arguments size the intermediates.
+ */
+int64_t pda_association_workspace_bytes(int64_t nProblems, int64_t totalCostElems, int64_t totalRows,
+                                        int64_t totalProbElems, int32_t k, int32_t maxNumRow, int32_t maxNumCol);
+int pda_association_probs_batch(const double* costs, const int64_t* costOff, const int32_t* nL, const int32_t* nM,
+                                const int64_t* rowOff, int64_t nProblems, int64_t totalCostElems, int64_t totalRows,
+                                int64_t totalProbElems, int32_t maxNumRow, int32_t maxNumCol, int32_t k,
+                                double* probs, const int64_t* probOff, int32_t* nFound,
+                                void* workspace, int64_t workspaceBytes, void* stream);
+int pda_association_probs_batch_host(const double* costs, const int64_t* costOff, const int32_t* nL, const int32_t* nM,
+                                     int64_t nProblems, int32_t k, double* probs, const int64_t* probOff,
+                                     int32_t device);
+
+/* ------------------------------------------------------------------------------------------
  * Matrix permanent, Nijenhuis-Wilf / Ryser over Gray-code column subsets.
  * Replaces permanentExactSquare / permanentExact (nwPerm.h:22-24; nwPerm.cpp:217-231, 251-332).
  *

@@ -37,6 +37,7 @@ class CpuChecker:
         f("assignment_prob", _int, [_ptr, _i64, _i64, _i64, _ptr])
         f("brute_force_prob", _int, [_ptr, _i64, _i64, _ptr])
         f("permanent_prob", _int, [_ptr, _i64, _i64, _int, _ptr])
+        f("association_probs", _int, [_ptr, _i64, _i64, _i64, _int, _ptr])
         f("permanent_exact", _dbl, [_ptr, _i64, _i64, _ptr])
         f("permanent_exact_square", _dbl, [_ptr, _i64, _ptr])
         f("permanent_exact_long", _dbl, [_ptr, _i64, _i64, _ptr])
@@ -121,6 +122,15 @@ class CpuChecker:
 
     def permanent_prob(self, cmat, nL, perm_opt=1):
         return self._probs(self._permanent_prob, cmat, nL, perm_opt)
+
+    def association_probs(self, cmat, nL, k, use_perm=False):
+        """getAssignmentProbs from the cost matrix on (assignment.cpp:57-74) -> (status, probs[nM, nL+1])."""
+        cmat = np.asfortranarray(cmat, dtype=np.float64)
+        nr, nc = cmat.shape
+        flat = np.ascontiguousarray(cmat.reshape(-1, order="F"))
+        out = np.zeros((nc, nL + 1))
+        st = self._association_probs(_p(flat), nL, nc, k, int(use_perm), _p(out))
+        return int(st), out
 
     # ---- permanents -------------------------------------------------------------
     def permanent_exact(self, a):

@@ -188,3 +188,26 @@ int orc_permanent_prob(const double* costsIn, int64_t nL, int64_t nM, int permOp
     free(P); free(S); free(others);
     return status;
 }
+
+/* The numeric body of getAssignmentProbs (assignment.cpp:57-74): condition the costs, compute the weights of the
+ * conditioned problem (k-best, or permanent-based when usePerm), scatter them back through rowIdx.
+ * probs is nM x (nL+1), row-major.  nL == 0 -> {1} per detection (:51-53). */
+int orc_association_probs(const double* costs, int64_t nL, int64_t nM, int64_t k, int usePerm, double* probs) {
+    if (nM <= 0) return 0;
+    if (nL == 0) { for (int64_t m = 0; m < nM; m++) probs[m] = 1.0; return 0; }
+    const int64_t nR = nL + nM, W = nL + 1;
+    double* cond = (double*)malloc((size_t)(nR * nM) * sizeof(double));
+    int64_t* rowIdx = (int64_t*)malloc((size_t)nR * sizeof(int64_t));
+    const int64_t good = orc_condition_costs(costs, nR, nM, cond, rowIdx);
+    const int64_t condL = good - nM; /* (conditionedCosts.size()/nM) - nM (:60) */
+    double* cp = (double*)malloc((size_t)(nM * (condL + 1)) * sizeof(double));
+    int status = usePerm ? orc_permanent_prob(cond, condL, nM, 1, cp) : orc_assignment_prob(cond, condL, nM, k, cp);
+    for (int64_t i = 0; i < nM * W; i++) probs[i] = 0;
+    if (!status)
+        for (int64_t m = 0; m < nM; m++) {
+            for (int64_t l = 0; l < condL; l++) probs[m * W + rowIdx[l]] = cp[m * (condL + 1) + l];
+            probs[m * W + nL] = cp[m * (condL + 1) + condL];
+        }
+    free(cond); free(rowIdx); free(cp);
+    return status;
+}

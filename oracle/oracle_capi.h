@@ -54,6 +54,9 @@ int orc_brute_force_prob(const double* costs, int64_t nL, int64_t nM, double* pr
 /* assignment.cpp:145-290 (+292-323, 325-435).  Returns 0, or 1 where the reference throws. */
 int orc_permanent_prob(const double* costs, int64_t nL, int64_t nM, int permOpt, double* probs);
 
+/* assignment.cpp:57-74 (getAssignmentProbs after the cost matrix has been built). Returns 0, or 1 where the reference throws. */
+int orc_association_probs(const double* costs, int64_t nL, int64_t nM, int64_t k, int usePerm, double* probs);
+
 /* nwPerm.cpp:217-231 / 251-332 / 386-400; status 1 where the reference throws (dim > 32). */
 double orc_permanent_exact(const double* A, int64_t rows, int64_t cols, int* status);
 double orc_permanent_exact_square(const double* A, int64_t n, int* status);

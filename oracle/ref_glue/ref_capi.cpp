@@ -160,6 +160,38 @@ int ref_permanent_prob(const double* costs, int64_t nL, int64_t nM, int permOpt,
     return a.status;
 }
 
+// getAssignmentProbs (assignment.cpp:38-139) takes GTSAM quadrics and cannot be compiled here; this is its
+// cost-matrix-level body, lines :57-74, written against the reference's own conditionCosts / assignmentProb /
+// permanentProb (the only restated part is the scatter loop :68-74).
+struct AssocArgs { const double* costs; int64_t nL, nM, k; int usePerm; double* probs; int status; };
+static void assocBody(void* p) {
+    AssocArgs* a = static_cast<AssocArgs*>(p);
+    const size_t nL = size_t(a->nL), nM = size_t(a->nM);
+    a->status = 0;
+    if (nM == 0) return;
+    if (nL == 0) { for (size_t m = 0; m < nM; m++) a->probs[m] = 1.0; return; }
+    try {
+        std::vector<double> costMatrix(a->costs, a->costs + (nL + nM) * nM);
+        std::vector<ptrdiff_t> rowIdx;
+        std::vector<double> conditionedCosts = conditionCosts(costMatrix, nL + nM, nM, rowIdx);
+        size_t condL = (conditionedCosts.size() / nM) - nM;
+        std::vector<std::vector<double> > conditionedProbs;
+        if (a->usePerm) conditionedProbs = permanentProb(conditionedCosts, condL, nM, 1);
+        else conditionedProbs = assignmentProb(conditionedCosts, condL, nM, size_t(a->k));
+        std::vector<std::vector<double> > probs(nM, std::vector<double>(nL + 1, 0));
+        for (size_t m = 0; m < nM; m++) {
+            for (size_t l = 0; l < condL; l++) probs[m][rowIdx[l]] = conditionedProbs[m][l];
+            probs[m][nL] = conditionedProbs[m][condL];
+        }
+        flattenProbs(probs, a->probs);
+    } catch (const std::exception&) { a->status = 1; }
+}
+int ref_association_probs(const double* costs, int64_t nL, int64_t nM, int64_t k, int usePerm, double* probs) {
+    AssocArgs a = {costs, nL, nM, k, usePerm, probs, 0};
+    runOnBigStack(assocBody, &a);
+    return a.status;
+}
+
 double ref_permanent_exact(const double* A, int64_t rows, int64_t cols, int* status) {
     try { *status = 0; return permanentExact(wrap(A, rows, cols)); }
     catch (const std::exception&) { *status = 1; return 0.0; }

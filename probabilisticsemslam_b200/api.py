@@ -169,6 +169,17 @@ def permanent_prob_batch(pb: ProblemBatch, perm_opt: int = 1, device: int = 0):
     return tabs, st
 
 
+def association_probs_batch(pb: ProblemBatch, k: int, device: int = 0) -> list[np.ndarray]:
+    """getAssignmentProbs from the cost matrices on (assignment.cpp:57-74, usePerm = 0), fused on the device:
+    conditionCosts -> assignmentProb -> scatter back through rowIdx.  Returns one (nM, nL+1) table per problem."""
+    n = len(pb)
+    nL, nM = pb.nL.astype(np.int32), pb.nM.astype(np.int32)
+    prob_off = _prefix(nM.astype(np.int64) * (nL.astype(np.int64) + 1))
+    probs = np.zeros(int((nM.astype(np.int64) * (nL.astype(np.int64) + 1)).sum()))
+    check(lib().pda_association_probs_batch_host(_p(pb.costs), _p(pb.cost_off), _p(nL), _p(nM), n, k, _p(probs), _p(prob_off), device))
+    return [probs[prob_off[p]:prob_off[p] + int(nM[p]) * (int(nL[p]) + 1)].reshape(int(nM[p]), int(nL[p]) + 1) for p in range(n)]
+
+
 def permanent_range(a: np.ndarray, begin: int, end: int, device: int = 0) -> tuple[float, float]:
     """Partial NW sum of one square matrix over Gray indices [begin, end) as (hi, lo)."""
     a = np.asarray(a, np.float64)
@@ -268,6 +279,23 @@ def bruteForceProb(C: np.ndarray, nL: int, device: int = 0) -> np.ndarray:
     k = 1 if C.shape[1] == 1 else brute_force_k(np.asarray(C, np.float64))
     r = murty_batch(pb, k, cut_mode=CUT_NONE, weight_mode=WEIGHTS_UNGATED, want_lists=False, device=device)
     return r.prob_table(pb, 0).copy()
+
+
+def getAssignmentProbsFromCosts(C: np.ndarray, nL: int, k: int, usePerm: bool = False, device: int = 0) -> np.ndarray:
+    """assignment.cpp:57-74: what getAssignmentProbs does once computeQuadricCostMatrix has produced C."""
+    C = np.asarray(C, np.float64)
+    if not usePerm:
+        return association_probs_batch(_one(C, nL), k, device)[0].copy()
+    nM = C.shape[1]
+    if nL == 0:
+        return np.ones((nM, 1))
+    cond, rows = conditionCosts(C, device)
+    condL = cond.shape[0] - nM
+    cp = permanentProb(cond, condL, 1, device)
+    out = np.zeros((nM, nL + 1))
+    out[:, rows[:condL]] = cp[:, :condL]
+    out[:, nL] = cp[:, condL]
+    return out
 
 
 def permanentProb(C: np.ndarray, nL: int, permOpt: int = 1, device: int = 0):

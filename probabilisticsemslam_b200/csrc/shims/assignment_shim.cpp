@@ -74,6 +74,31 @@ std::vector<std::vector<double> > permanentProb(std::vector<double> costMatrix, 
     return unflatten(probs, nM, nL + 1);
 }
 
+std::vector<std::vector<double> > getAssignmentProbsFromCosts(const std::vector<double>& costMatrix, size_t nL, size_t nM,
+                                                              size_t k, bool usePerm) {
+    if (nM == 0) return std::vector<std::vector<double> >();
+    if (!usePerm) {  // one fused device pipeline
+        const int64_t costOff = 0, probOff = 0;
+        const int32_t nl = int32_t(nL), nm = int32_t(nM);
+        std::vector<double> probs(nM * (nL + 1), 0.0);
+        pdaCheck(pda_association_probs_batch_host(costMatrix.data(), &costOff, &nl, &nm, 1, int32_t(k), probs.data(), &probOff,
+                                                  pdaShimDevice()),
+                 "getAssignmentProbsFromCosts");
+        return unflatten(probs, nM, nL + 1);
+    }
+    if (nL == 0) return std::vector<std::vector<double> >(nM, std::vector<double>{1});
+    std::vector<ptrdiff_t> rowIdx;
+    std::vector<double> cond = conditionCosts(costMatrix, nL + nM, nM, rowIdx);
+    const size_t condL = (cond.size() / nM) - nM;
+    std::vector<std::vector<double> > cp = permanentProb(cond, condL, nM, 1);
+    std::vector<std::vector<double> > probs(nM, std::vector<double>(nL + 1, 0));
+    for (size_t m = 0; m < nM; m++) {
+        for (size_t l = 0; l < condL; l++) probs[m][size_t(rowIdx[l])] = cp[m][l];
+        probs[m][nL] = cp[m][condL];
+    }
+    return probs;
+}
+
 std::vector<double> conditionCosts(const std::vector<double>& costs, size_t nRows, size_t nCols,
                                    std::vector<ptrdiff_t>& rowIdxOut) {
     const int64_t costOff = 0, rowOff = 0;

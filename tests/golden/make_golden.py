@@ -148,6 +148,19 @@ def main():
     np.savez_compressed(os.path.join(OUT, "toprobs.npz"), n=np.int64(3), **{f"in{i}": v[i] for i in range(3)},
                         **{f"out{i}": R.to_probs(v[i]) for i in range(3)})
 
+    # --- getAssignmentProbs from the cost matrix on (assignment.cpp:57-74) ---------------------------------------
+    a = {"n": np.int64(16)}
+    for p in range(16):
+        a[f"C{p}"] = g2.matrix(p)
+        st_, pr = R.association_probs(g2.matrix(p), 30, 200, False)
+        assert st_ == 0
+        a[f"k200_{p}"] = pr
+        if cond[p][0].shape[0] <= 20:
+            st_, pr = R.association_probs(g2.matrix(p), 30, 200, True)
+            assert st_ == 0
+            a[f"perm_{p}"] = pr
+    np.savez_compressed(os.path.join(OUT, "association_g2.npz"), **a)
+
     # --- permanents ------------------------------------------------------------------------------------
     pm = {}
     dims = list(range(1, 21)) + [22]

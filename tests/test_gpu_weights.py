@@ -75,3 +75,28 @@ def test_weights_batch_vs_oracle(gpu_api, oracle):
         if cond.matrix(p).shape[0] <= 16:
             truth = oracle.brute_force_prob(cond.matrix(p), int(cond.nL[p]))
             assert np.max(np.abs(r.prob_table(cond, p) - truth)) < 0.1  # comparison.cpp:319
+
+
+def test_association_probs_fused_pipeline(gpu_api, oracle):
+    """getAssignmentProbs from the cost matrix on (assignment.cpp:57-74): conditionCosts -> assignmentProb ->
+    scatter through rowIdx, as one device-side pipeline."""
+    z = golden("association_g2")
+    n = int(z["n"])
+    pb = synth.pack([z[f"C{p}"] for p in range(n)], [30] * n)
+    tabs = gpu_api.association_probs_batch(pb, 200)
+    for p in range(n):
+        np.testing.assert_allclose(tabs[p], z[f"k200_{p}"], rtol=RTOL, atol=0)
+        if f"perm_{p}" in z:
+            got = gpu_api.getAssignmentProbsFromCosts(z[f"C{p}"], 30, 200, usePerm=True)
+            np.testing.assert_allclose(got, z[f"perm_{p}"], rtol=1e-6, atol=1e-300)   # NW cancellation: see test_gpu_permanent
+    # a bigger ragged batch against the oracle, including problems without landmarks and with one detection
+    g2 = synth.g2_gated(300, first=4000)
+    mats = [g2.matrix(p) for p in range(300)] + [np.array([[10.0, np.inf], [np.inf, 10.0]]), np.array([[3.0], [50.0], [10.0]])]
+    nls = [30] * 300 + [0, 2]
+    pb = synth.pack(mats, nls)
+    tabs = gpu_api.association_probs_batch(pb, 200)
+    for p in range(len(pb)):
+        st, want = oracle.association_probs(mats[p], nls[p], 200, False)
+        assert st == 0
+        np.testing.assert_allclose(tabs[p], want, rtol=RTOL, atol=0)
+        assert abs(tabs[p].sum(axis=1) - 1.0).max() < 1e-12

@@ -83,6 +83,21 @@ def test_weights(oracle):
         np.testing.assert_allclose(oracle.to_probs(z[f"in{i}"]), z[f"out{i}"], rtol=1e-14, atol=0)
 
 
+def test_association_probs(oracle):
+    z = golden("association_g2")
+    for p in range(int(z["n"])):
+        st, pr = oracle.association_probs(z[f"C{p}"], 30, 200, False)
+        assert st == 0
+        np.testing.assert_allclose(pr, z[f"k200_{p}"], rtol=1e-13, atol=0)
+        if f"perm_{p}" in z:
+            st, pr = oracle.association_probs(z[f"C{p}"], 30, 200, True)
+            assert st == 0
+            np.testing.assert_allclose(pr, z[f"perm_{p}"], rtol=1e-13, atol=0)
+    # no landmarks: every detection is "not assigned" with probability one (assignment.cpp:51-53)
+    st, pr = oracle.association_probs(np.array([[10.0, np.inf], [np.inf, 10.0]]), 0, 5)
+    assert st == 0 and pr.tolist() == [[1.0], [1.0]]
+
+
 def test_permanents(oracle):
     z = golden("permanent")
     for n in z["dims"]:
