@@ -49,6 +49,7 @@ int current_device_info(DeviceInfo* out) {
 
 std::mutex g_hostMu;
 std::vector<DevArena> g_arenas;
+std::vector<HostStreams> g_hostStreams;
 
 }  // namespace pda
 
@@ -193,31 +194,82 @@ int pda_murty_batch_host(const double* costs, const int64_t* costOff, const int3
     const size_t oProb = st.reserve(nProb * 8), oProbOff = st.reserve(n * 8), oNL = st.reserve(n * 4);
     const size_t oWs = st.reserve((size_t)wsBytes);
     PDA_TRY(st.commit());
-    cudaStream_t s = 0;
-    PDA_TRY(h2d(st.at<double>(oCost), costs, nCost, s));
-    PDA_TRY(h2d(st.at<int64_t>(oCostOff), costOff, n, s));
-    PDA_TRY(h2d(st.at<int32_t>(oNR), numRow, n, s));
-    PDA_TRY(h2d(st.at<int32_t>(oNC), numCol, n, s));
-    if (row4colBest) PDA_TRY(h2d(st.at<int64_t>(oR4cOff), r4cOff, n, s));
-    if (col4rowBest) PDA_TRY(h2d(st.at<int64_t>(oC4rOff), c4rOff, n, s));
-    if (weightMode) {
-        PDA_TRY(h2d(st.at<int64_t>(oProbOff), probOff, n, s));
-        PDA_TRY(h2d(st.at<int32_t>(oNL), nL, n, s));
+
+    // Large batches are cut into chunks that flow through three streams (copy in / run / copy out), so the PCIe
+    // transfers of one chunk overlap the kernel of another.  That needs every offset array to be non-decreasing
+    // (then a chunk's inputs and outputs are contiguous ranges); otherwise, and for small batches, one chunk.
+    bool monotonic = true;
+    for (size_t p = 1; p < n && monotonic; ++p) {
+        if (costOff[p] < costOff[p - 1]) monotonic = false;
+        if (row4colBest && r4cOff[p] < r4cOff[p - 1]) monotonic = false;
+        if (col4rowBest && c4rOff[p] < c4rOff[p - 1]) monotonic = false;
+        if (weightMode && probOff[p] < probOff[p - 1]) monotonic = false;
     }
-    PDA_TRY(pda_murty_batch(st.at<double>(oCost), st.at<int64_t>(oCostOff), st.at<int32_t>(oNR), st.at<int32_t>(oNC),
-                            nProblems, maxR, maxC, k, cutMode, cutoff, maximize, cutMaximize,
-                            row4colBest ? st.at<int64_t>(oR4c) : nullptr, st.at<int64_t>(oR4cOff),
-                            col4rowBest ? st.at<int64_t>(oC4r) : nullptr, st.at<int64_t>(oC4rOff),
-                            gainBest ? st.at<double>(oGain) : nullptr, st.at<int32_t>(oFound),
-                            weightMode, weightMode ? st.at<double>(oProb) : nullptr, st.at<int64_t>(oProbOff),
-                            st.at<int32_t>(oNL), st.at<unsigned char>(oWs), wsBytes, s));
-    PDA_TRY(d2h(row4colBest, st.at<int64_t>(oR4c), nR4c, s));
-    PDA_TRY(d2h(col4rowBest, st.at<int64_t>(oC4r), nC4r, s));
-    PDA_TRY(d2h(gainBest, st.at<double>(oGain), n * k, s));
-    PDA_TRY(d2h(nFound, st.at<int32_t>(oFound), n, s));
-    if (weightMode) PDA_TRY(d2h(probs, st.at<double>(oProb), nProb, s));
-    PDA_CUDA_TRY(cudaStreamSynchronize(s));
-    return PDA_OK;
+    // A chunk must stay large (>= 64k problems, ~18 per resident warp): every launch ends with a tail in which the
+    // persistent warps run dry one by one, and at 12.5k problems per chunk that cost more than the overlap gained
+    // (measured: 100k problems in 8 chunks, e2e 1.70 M/s vs 1.92 M/s unchunked).
+    const size_t nChunks = monotonic ? std::max<size_t>(1, std::min<size_t>(8, n / 65536)) : 1;
+    HostStreams* hs = nullptr;
+    PDA_TRY(host_streams(device, &hs));
+    cudaStream_t sIn = hs->in, sRun = hs->run, sOut = hs->out;
+    std::vector<cudaEvent_t> evIn(nChunks), evRun(nChunks);
+    for (size_t c = 0; c < nChunks; ++c) {
+        PDA_CUDA_TRY(cudaEventCreateWithFlags(&evIn[c], cudaEventDisableTiming));
+        PDA_CUDA_TRY(cudaEventCreateWithFlags(&evRun[c], cudaEventDisableTiming));
+    }
+    int rc = PDA_OK;
+    auto body = [&]() -> int {
+        PDA_TRY(h2d(st.at<int64_t>(oCostOff), costOff, n, sIn));
+        PDA_TRY(h2d(st.at<int32_t>(oNR), numRow, n, sIn));
+        PDA_TRY(h2d(st.at<int32_t>(oNC), numCol, n, sIn));
+        if (row4colBest) PDA_TRY(h2d(st.at<int64_t>(oR4cOff), r4cOff, n, sIn));
+        if (col4rowBest) PDA_TRY(h2d(st.at<int64_t>(oC4rOff), c4rOff, n, sIn));
+        if (weightMode) {
+            PDA_TRY(h2d(st.at<int64_t>(oProbOff), probOff, n, sIn));
+            PDA_TRY(h2d(st.at<int32_t>(oNL), nL, n, sIn));
+        }
+        for (size_t c = 0; c < nChunks; ++c) {
+            const size_t p0 = n * c / nChunks, p1 = n * (c + 1) / nChunks, m = p1 - p0;
+            const bool last = (p1 == n);
+            // copy in: this chunk's cost matrices
+            const size_t c0 = nChunks == 1 ? 0 : (size_t)costOff[p0], c1 = (nChunks == 1 || last) ? nCost : (size_t)costOff[p1];
+            PDA_TRY(h2d(st.at<double>(oCost) + c0, costs + c0, c1 - c0, sIn));
+            PDA_CUDA_TRY(cudaEventRecord(evIn[c], sIn));
+            // run
+            PDA_CUDA_TRY(cudaStreamWaitEvent(sRun, evIn[c], 0));
+            PDA_TRY(pda_murty_batch(st.at<double>(oCost), st.at<int64_t>(oCostOff) + p0, st.at<int32_t>(oNR) + p0,
+                                    st.at<int32_t>(oNC) + p0, (int64_t)m, maxR, maxC, k, cutMode, cutoff, maximize, cutMaximize,
+                                    row4colBest ? st.at<int64_t>(oR4c) : nullptr, st.at<int64_t>(oR4cOff) + p0,
+                                    col4rowBest ? st.at<int64_t>(oC4r) : nullptr, st.at<int64_t>(oC4rOff) + p0,
+                                    gainBest ? st.at<double>(oGain) + p0 * (size_t)k : nullptr, st.at<int32_t>(oFound) + p0,
+                                    weightMode, weightMode ? st.at<double>(oProb) : nullptr, st.at<int64_t>(oProbOff) + p0,
+                                    st.at<int32_t>(oNL) + p0, st.at<unsigned char>(oWs), wsBytes, sRun));
+            PDA_CUDA_TRY(cudaEventRecord(evRun[c], sRun));
+            // copy out: this chunk's results
+            PDA_CUDA_TRY(cudaStreamWaitEvent(sOut, evRun[c], 0));
+            if (row4colBest) {
+                const size_t a0 = nChunks == 1 ? 0 : (size_t)r4cOff[p0], a1 = (nChunks == 1 || last) ? nR4c : (size_t)r4cOff[p1];
+                PDA_TRY(d2h(row4colBest + a0, st.at<int64_t>(oR4c) + a0, a1 - a0, sOut));
+            }
+            if (col4rowBest) {
+                const size_t a0 = nChunks == 1 ? 0 : (size_t)c4rOff[p0], a1 = (nChunks == 1 || last) ? nC4r : (size_t)c4rOff[p1];
+                PDA_TRY(d2h(col4rowBest + a0, st.at<int64_t>(oC4r) + a0, a1 - a0, sOut));
+            }
+            if (gainBest) PDA_TRY(d2h(gainBest + p0 * (size_t)k, st.at<double>(oGain) + p0 * (size_t)k, m * (size_t)k, sOut));
+            PDA_TRY(d2h(nFound + p0, st.at<int32_t>(oFound) + p0, m, sOut));
+            if (weightMode) {
+                const size_t a0 = nChunks == 1 ? 0 : (size_t)probOff[p0], a1 = (nChunks == 1 || last) ? nProb : (size_t)probOff[p1];
+                PDA_TRY(d2h(probs + a0, st.at<double>(oProb) + a0, a1 - a0, sOut));
+            }
+        }
+        PDA_CUDA_TRY(cudaStreamSynchronize(sOut));
+        PDA_CUDA_TRY(cudaStreamSynchronize(sRun));
+        PDA_CUDA_TRY(cudaStreamSynchronize(sIn));
+        return PDA_OK;
+    };
+    rc = body();
+    for (size_t c = 0; c < nChunks; ++c) { cudaEventDestroy(evIn[c]); cudaEventDestroy(evRun[c]); }
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------- LAP

@@ -45,6 +45,22 @@ private:
     int device_; size_t used_; unsigned char* base_;
 };
 
+// three non-blocking streams per device for the chunked host path: copy in / run / copy out
+struct HostStreams { int device; cudaStream_t in, run, out; };
+extern std::vector<HostStreams> g_hostStreams;
+inline int host_streams(int device, HostStreams** out) {
+    for (HostStreams& h : g_hostStreams)
+        if (h.device == device) { *out = &h; return PDA_OK; }
+    HostStreams h;
+    h.device = device;
+    PDA_CUDA_TRY(cudaStreamCreateWithFlags(&h.in, cudaStreamNonBlocking));
+    PDA_CUDA_TRY(cudaStreamCreateWithFlags(&h.run, cudaStreamNonBlocking));
+    PDA_CUDA_TRY(cudaStreamCreateWithFlags(&h.out, cudaStreamNonBlocking));
+    g_hostStreams.push_back(h);
+    *out = &g_hostStreams.back();
+    return PDA_OK;
+}
+
 inline int check_device(int device) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
