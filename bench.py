@@ -325,7 +325,7 @@ def main():
                 "call": "pda_murty_batch_host (batched assignmentProb: host cost matrices in, host weights out; "
                         "k-best lists stay device-internal as they are stack temporaries in the reference)",
                 "matches_device_run": e2e_matches},
-        "gpu_launches": args.steps,
+        "gpu_launches": 2 * args.steps,  # per step: order_by_cost_kernel + murty_kernel<2>
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
                      "traffic": measured_traffic(n, k), "peak_source": pk_kind, "kernel": "murty_kernel<2>", "kernel_ms": kernel_ms,
                      "algorithmic_bytes_per_launch": alg_bytes,

@@ -104,6 +104,9 @@ int pda_device_count(void) {
 }
 
 // ---------------------------------------------------------------------------------------- Murty
+// room for the cost-ordered problem list at the tail of the workspace (only worth it when warps take several problems)
+static int64_t order_bytes(int64_t nProblems) { return (nProblems + 63) / 64 * 256; }
+
 static int64_t murty_full_warps(const MurtyGeometry& g, const DeviceInfo& dev) {
     return (int64_t)dev.smCount * g.ctasPerSm * g.warpsPerCta;
 }
@@ -116,7 +119,7 @@ int64_t pda_murty_workspace_bytes(int64_t nProblems, int32_t k, int32_t maxNumRo
     rc = murty_geometry(k, maxNumRow, maxNumCol, false, dev, &g);
     if (rc) return rc;
     int64_t warps = std::min<int64_t>(std::max<int64_t>(nProblems, 1), murty_full_warps(g, dev));
-    return 256 + warps * g.arenaStride;
+    return 256 + warps * g.arenaStride + order_bytes(nProblems);
 }
 
 int pda_murty_batch(const double* costs, const int64_t* costOff, const int32_t* numRow, const int32_t* numCol,
@@ -140,7 +143,10 @@ int pda_murty_batch(const double* costs, const int64_t* costOff, const int32_t* 
     MurtyArgs a;
     PDA_TRY(murty_geometry(k, maxNumRow, maxNumCol, weightMode != 0, dev, &a.geo));
     int64_t warps = std::min<int64_t>(nProblems, murty_full_warps(a.geo, dev));
-    warps = std::min<int64_t>(warps, (workspaceBytes - 256) / a.geo.arenaStride);
+    // the cost-ordered list goes behind the arenas when the workspace has room for it and there is a tail to shorten
+    const bool ordered = nProblems > 2 * warps && nProblems < (1LL << 31) &&
+                         workspaceBytes >= 256 + warps * a.geo.arenaStride + order_bytes(nProblems);
+    warps = std::min<int64_t>(warps, (workspaceBytes - 256 - (ordered ? order_bytes(nProblems) : 0)) / a.geo.arenaStride);
     if (warps < 1) return fail(PDA_ERR_WORKSPACE, "murty: workspace of %lld B holds no arena (%lld B each)",
                                (long long)workspaceBytes, (long long)a.geo.arenaStride);
     a.costs = costs; a.costOff = costOff; a.numRow = numRow; a.numCol = numCol; a.nProblems = nProblems;
@@ -152,6 +158,7 @@ int pda_murty_batch(const double* costs, const int64_t* costOff, const int32_t* 
     a.cursor = reinterpret_cast<unsigned long long*>(workspace);
     a.arena = reinterpret_cast<unsigned char*>(workspace) + 256;
     a.nWarps = (int32_t)warps;
+    a.order = ordered ? reinterpret_cast<int32_t*>(a.arena + warps * a.geo.arenaStride) : nullptr;
     return launch_murty(a, reinterpret_cast<cudaStream_t>(stream));
 }
 

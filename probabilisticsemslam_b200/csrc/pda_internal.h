@@ -56,6 +56,7 @@ struct MurtyArgs {
     double* probs; const int64_t* probOff; const int32_t* nL;
     unsigned char* arena;
     unsigned long long* cursor;  // work-queue cursor (zeroed before launch)
+    int32_t* order;              // optional: problem indices, most expensive first (NULL = index order)
     int32_t nWarps;              // arenas available == warps allowed to run
     MurtyGeometry geo;
 };
