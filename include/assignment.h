@@ -38,6 +38,11 @@ void toProbs(std::vector<double>& costMatrix);
 std::vector<std::vector<double> > getAssignmentProbsFromCosts(const std::vector<double>& costMatrix, size_t nL, size_t nM,
                                                               size_t k, bool usePerm);
 
+/* asgnBB (reference assignment.h:21, assignment.cpp:724-775) on raw boxes: five doubles per box
+ * (xmin, ymin, xmax, ymax, xOffset), nonassign = runConsts.NONASSIGN_BOUNDBOX.  Returns, per left box, the index of
+ * the right box it is paired with or -1.  A boundBox-typed asgnBB is a three-line wrapper over this. */
+std::vector<int> asgnBBRaw(const std::vector<double>& boxesL, const std::vector<double>& boxesR, double nonassign);
+
 /* raw form of conditionedPermanent: A is rows x cols, column-major */
 double conditionedPermanentRaw(const double* A, size_t rows, size_t cols, int permOpt);
 #ifdef PDA_HAVE_EIGEN

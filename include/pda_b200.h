@@ -145,6 +145,16 @@ int pda_association_probs_batch_host(const double* costs, const int64_t* costOff
                                      int32_t device);
 
 /* ------------------------------------------------------------------------------------------
+ * Stereo bounding-box association: asgnBB (assignment.h:21, assignment.cpp:724-775) with computeBBCostMatrix
+ * (:777-797) and boundBox::IoU (boundBox.h:62-75), for a batch of frames.  A box is five doubles
+ * (xmin, ymin, xmax, ymax, xOffset); frame f owns left boxes [offL[f], offL[f+1]) and right boxes
+ * [offR[f], offR[f+1]) (offL/offR have nFrames+1 entries).  assignment[i] = index (within its frame) of the right
+ * box paired with left box i, or -1.  nonassign = NONASSIGN_BOUNDBOX.
+ */
+int pda_asgn_bb_batch_host(const double* boxesL, const int64_t* offL, const double* boxesR, const int64_t* offR,
+                           int64_t nFrames, double nonassign, int32_t* assignment, int32_t device);
+
+/* ------------------------------------------------------------------------------------------
  * Matrix permanent, Nijenhuis-Wilf / Ryser over Gray-code column subsets.
  * Replaces permanentExactSquare / permanentExact (nwPerm.h:22-24; nwPerm.cpp:217-231, 251-332).
  *

@@ -44,6 +44,8 @@ class CpuChecker:
         f("conditioned_permanent", _dbl, [_ptr, _i64, _i64, _int, _ptr])
         f("batch", _dbl, [_ptr, _ptr, _ptr, _ptr, _i64, _i64, _dbl, _int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr])
         f("permanent_batch", _dbl, [_ptr, _i64, _i64, _int, _ptr])
+        f("bb_cost_matrix", None, [_ptr, C.c_long, _ptr, C.c_long, _dbl, _ptr])
+        f("asgn_bb", None, [_ptr, C.c_long, _ptr, C.c_long, _dbl, _ptr])
 
     def _fn(self, name, res, args):
         fn = getattr(self.lib, f"{self.prefix}_{name}")
@@ -160,6 +162,19 @@ class CpuChecker:
         flat = np.ascontiguousarray(a.reshape(-1, order="F"))
         r = self._conditioned_permanent(_p(flat), a.shape[0], a.shape[1], perm_opt, C.byref(st))
         return float(r), st.value
+
+    # ---- stereo box association (boxes: [n, 5] = xmin, ymin, xmax, ymax, xOffset) -----------------------
+    def bb_cost_matrix(self, boxes_l, boxes_r, nonassign):
+        bl, br = np.ascontiguousarray(boxes_l, np.float64).reshape(-1, 5), np.ascontiguousarray(boxes_r, np.float64).reshape(-1, 5)
+        out = np.zeros((bl.shape[0] + br.shape[0]) * bl.shape[0])
+        self._bb_cost_matrix(_p(bl), bl.shape[0], _p(br), br.shape[0], float(nonassign), _p(out))
+        return out.reshape((bl.shape[0] + br.shape[0], bl.shape[0]), order="F")
+
+    def asgn_bb(self, boxes_l, boxes_r, nonassign):
+        bl, br = np.ascontiguousarray(boxes_l, np.float64).reshape(-1, 5), np.ascontiguousarray(boxes_r, np.float64).reshape(-1, 5)
+        out = np.full(max(bl.shape[0], 1), -7, np.int32)
+        self._asgn_bb(_p(bl), bl.shape[0], _p(br), br.shape[0], float(nonassign), _p(out))
+        return out[:bl.shape[0]]
 
     # ---- batches (timing + bulk checks) ----------------------------------------------
     def batch(self, pb, k, *, cutoff=42.0, threads=1, want_probs=True, want_lists=True):

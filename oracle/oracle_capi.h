@@ -64,6 +64,10 @@ double orc_permanent_exact_long(const double* A, int64_t rows, int64_t cols, int
 /* assignment.cpp:325-435; status 1 where the reference throws (bad permOpt, or permOpt 0 = Huber, out of scope). */
 double orc_conditioned_permanent(const double* A, int64_t rows, int64_t cols, int permOpt, int* status);
 
+/* Stereo box association: boundBox.h:62-75, assignment.cpp:724-797.  A box = xmin, ymin, xmax, ymax, xOffset. */
+void orc_bb_cost_matrix(const double* boxesL, int64_t nL, const double* boxesR, int64_t nR, double nonassign, double* out);
+void orc_asgn_bb(const double* boxesL, int64_t nL, const double* boxesR, int64_t nR, double nonassign, int32_t* out);
+
 /* Batch drivers for CPU-baseline timing: problems [0,n) over nThreads host threads,
  * returns wall seconds.  probs != NULL -> assignmentProb per problem;
  * gain != NULL -> kBest2DCutoff lists (minimise). */

@@ -35,6 +35,7 @@ SIGNATURES = {
     "pda_association_workspace_bytes": (i64, [i64, i64, i64, i64, i32, i32, i32]),
     "pda_association_probs_batch": (C.c_int, [ptr, ptr, ptr, ptr, ptr, i64, i64, i64, i64, i32, i32, i32, ptr, ptr, ptr, ptr, i64, ptr]),
     "pda_association_probs_batch_host": (C.c_int, [ptr, ptr, ptr, ptr, i64, i32, ptr, ptr, i32]),
+    "pda_asgn_bb_batch_host": (C.c_int, [ptr, ptr, ptr, ptr, i64, dbl, ptr, i32]),
     "pda_permanent_workspace_bytes": (i64, [i64]),
     "pda_permanent_batch": (C.c_int, [ptr, ptr, ptr, ptr, i64, i32, ptr, ptr, ptr, i64, ptr]),
     "pda_permanent_batch_host": (C.c_int, [ptr, ptr, ptr, ptr, i64, ptr, ptr, i32]),

@@ -180,6 +180,27 @@ def association_probs_batch(pb: ProblemBatch, k: int, device: int = 0) -> list[n
     return [probs[prob_off[p]:prob_off[p] + int(nM[p]) * (int(nL[p]) + 1)].reshape(int(nM[p]), int(nL[p]) + 1) for p in range(n)]
 
 
+def asgn_bb_batch(boxes_l: list[np.ndarray], boxes_r: list[np.ndarray], nonassign: float, device: int = 0) -> list[np.ndarray]:
+    """asgnBB (assignment.cpp:724-775) for a batch of frames; boxes are [count, 5] = xmin, ymin, xmax, ymax, xOffset.
+    Returns per frame the right-box index paired with each left box (-1 = none)."""
+    n = len(boxes_l)
+    cl = np.asarray([len(b) for b in boxes_l], np.int64)
+    cr = np.asarray([len(b) for b in boxes_r], np.int64)
+    off_l = np.concatenate([[0], np.cumsum(cl)]).astype(np.int64)
+    off_r = np.concatenate([[0], np.cumsum(cr)]).astype(np.int64)
+    flat_l = np.ascontiguousarray(np.concatenate([np.asarray(b, np.float64).reshape(-1, 5) for b in boxes_l] + [np.zeros((0, 5))]))
+    flat_r = np.ascontiguousarray(np.concatenate([np.asarray(b, np.float64).reshape(-1, 5) for b in boxes_r] + [np.zeros((0, 5))]))
+    out = np.full(max(int(off_l[-1]), 1), -7, np.int32)
+    check(lib().pda_asgn_bb_batch_host(_p(flat_l) if flat_l.size else None, _p(off_l), _p(flat_r) if flat_r.size else None,
+                                       _p(off_r), n, float(nonassign), _p(out), device))
+    return [out[off_l[f]:off_l[f + 1]].copy() for f in range(n)]
+
+
+def asgnBB(bbL: np.ndarray, bbR: np.ndarray, nonassign: float, device: int = 0) -> np.ndarray:
+    """assignment.h:21 for one frame."""
+    return asgn_bb_batch([np.asarray(bbL, np.float64).reshape(-1, 5)], [np.asarray(bbR, np.float64).reshape(-1, 5)], nonassign, device)[0]
+
+
 def permanent_range(a: np.ndarray, begin: int, end: int, device: int = 0) -> tuple[float, float]:
     """Partial NW sum of one square matrix over Gray indices [begin, end) as (hi, lo)."""
     a = np.asarray(a, np.float64)

@@ -99,6 +99,13 @@ std::vector<std::vector<double> > getAssignmentProbsFromCosts(const std::vector<
     return probs;
 }
 
+std::vector<int> asgnBBRaw(const std::vector<double>& boxesL, const std::vector<double>& boxesR, double nonassign) {
+    const int64_t offL[2] = {0, int64_t(boxesL.size() / 5)}, offR[2] = {0, int64_t(boxesR.size() / 5)};
+    std::vector<int32_t> a(size_t(offL[1]) ? size_t(offL[1]) : 1, -1);
+    pdaCheck(pda_asgn_bb_batch_host(boxesL.data(), offL, boxesR.data(), offR, 1, nonassign, a.data(), pdaShimDevice()), "asgnBB");
+    return std::vector<int>(a.begin(), a.begin() + offL[1]);
+}
+
 std::vector<double> conditionCosts(const std::vector<double>& costs, size_t nRows, size_t nCols,
                                    std::vector<ptrdiff_t>& rowIdxOut) {
     const int64_t costOff = 0, rowOff = 0;

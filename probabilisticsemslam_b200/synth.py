@@ -163,3 +163,30 @@ def dense_square(n_mats: int, dim: int, *, first: int = 0, seed: int = SEED + 2)
     returned as float64[n_mats, dim*dim]."""
     ids = np.arange(first, first + n_mats, dtype=np.uint64)
     return np.ascontiguousarray(u01(stream(ids, dim * dim, seed)))
+
+
+def stereo_boxes(n: int, *, first: int = 0, seed: int = SEED + 3):
+    """Stereo detection pairs for the box association (asgnBB): per problem a list of right-image boxes in a
+    1242 x 375 frame and the left-image boxes they came from (shifted by a disparity, jittered, some dropped, some
+    spurious), as [count, 5] arrays (xmin, ymin, xmax, ymax, xOffset).  xOffset is the per-box stereo offset estimate
+    the reference adds to the box the IoU is called on (boundBox.h:63-64).  Returns (list_left, list_right)."""
+    ids = np.arange(first, first + n, dtype=np.uint64)
+    u = u01(stream(ids, 2 + 12 * 8, seed))
+    lefts, rights = [], []
+    for p in range(n):
+        nr = 1 + int(u[p, 0] * 10) % 10
+        disp = 5.0 + 60.0 * u[p, 1]
+        r = u[p, 2:].reshape(12, 8)
+        R, L = [], []
+        for i in range(nr):
+            x0, y0 = 1100.0 * r[i, 0], 300.0 * r[i, 1]
+            w, h = 30.0 + 140.0 * r[i, 2], 20.0 + 55.0 * r[i, 3]
+            R.append([x0, y0, x0 + w, y0 + h, disp * (1.0 + 0.1 * (r[i, 4] - 0.5))])
+            if r[i, 5] < 0.85:  # seen in the left image too
+                j = 6.0 * (r[i, 6:8] - 0.5)
+                L.append([x0 + disp + j[0], y0 + j[1], x0 + w + disp + j[0], y0 + h + j[1], -disp * (1.0 + 0.1 * (r[i, 4] - 0.5))])
+        if r[10, 0] < 0.3:  # a spurious left detection
+            L.append([1000.0 * r[10, 1], 250.0 * r[10, 2], 1000.0 * r[10, 1] + 60.0, 250.0 * r[10, 2] + 40.0, -disp])
+        lefts.append(np.asarray(L, dtype=np.float64).reshape(-1, 5))
+        rights.append(np.asarray(R, dtype=np.float64).reshape(-1, 5))
+    return lefts, rights

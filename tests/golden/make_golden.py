@@ -161,6 +161,16 @@ def main():
             a[f"perm_{p}"] = pr
     np.savez_compressed(os.path.join(OUT, "association_g2.npz"), **a)
 
+    # --- stereo box association: asgnBB + computeBBCostMatrix + boundBox::IoU (reference's own code) ---------------
+    L, Rt = synth.stereo_boxes(40)
+    bb = {"n": np.int64(40), "nonassign": np.float64(0.6)}
+    for i in range(40):
+        bb[f"L{i}"], bb[f"R{i}"] = L[i], Rt[i]
+        bb[f"a{i}"] = R.asgn_bb(L[i], Rt[i], 0.6)
+        if len(L[i]) and len(Rt[i]):
+            bb[f"C{i}"] = R.bb_cost_matrix(L[i], Rt[i], 0.6)
+    np.savez_compressed(os.path.join(OUT, "asgn_bb.npz"), **bb)
+
     # --- permanents ------------------------------------------------------------------------------------
     pm = {}
     dims = list(range(1, 21)) + [22]

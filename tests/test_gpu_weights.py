@@ -100,3 +100,21 @@ def test_association_probs_fused_pipeline(gpu_api, oracle):
         assert st == 0
         np.testing.assert_allclose(tabs[p], want, rtol=RTOL, atol=0)
         assert abs(tabs[p].sum(axis=1) - 1.0).max() < 1e-12
+
+
+def test_stereo_box_association(gpu_api, oracle):
+    """asgnBB (assignment.cpp:724-775): IoU scores, dummy diagonal, k = 1 maximising LAP, as one device pipeline."""
+    z = golden("asgn_bb")
+    n = int(z["n"])
+    got = gpu_api.asgn_bb_batch([z[f"L{i}"] for i in range(n)], [z[f"R{i}"] for i in range(n)], float(z["nonassign"]))
+    for i in range(n):
+        np.testing.assert_array_equal(got[i], z[f"a{i}"])
+    L, R = synth.stereo_boxes(2000, first=50_000)
+    got = gpu_api.asgn_bb_batch(L, R, 0.2)
+    matched = 0
+    for i in range(len(L)):
+        want = oracle.asgn_bb(L[i], R[i], 0.2)
+        np.testing.assert_array_equal(got[i], want)
+        matched += int((want >= 0).sum())
+    assert matched > 1000
+    np.testing.assert_array_equal(gpu_api.asgnBB(L[3], R[3], 0.2), oracle.asgn_bb(L[3], R[3], 0.2))

@@ -98,6 +98,15 @@ def test_association_probs(oracle):
     assert st == 0 and pr.tolist() == [[1.0], [1.0]]
 
 
+def test_stereo_box_association(oracle):
+    z = golden("asgn_bb")
+    for i in range(int(z["n"])):
+        np.testing.assert_array_equal(oracle.asgn_bb(z[f"L{i}"], z[f"R{i}"], float(z["nonassign"])), z[f"a{i}"])
+        if f"C{i}" in z:
+            np.testing.assert_array_equal(bits(np.nan_to_num(oracle.bb_cost_matrix(z[f"L{i}"], z[f"R{i}"], float(z["nonassign"])), neginf=-1.0)),
+                                          bits(np.nan_to_num(z[f"C{i}"], neginf=-1.0)))
+
+
 def test_permanents(oracle):
     z = golden("permanent")
     for n in z["dims"]:
