@@ -233,3 +233,47 @@ def test_full_size_properties(gpu_api):
         for p in sel[:50]:
             t = probs[int(plan.prob_off_h[p]):int(plan.prob_off_h[p]) + m * 31].view(m, 31)
             assert bool(((t.sum(dim=1) - 1.0).abs() < 1e-12).all())
+
+
+def test_c_abi_error_paths(gpu_api):
+    """Bad arguments come back as negative status codes with a message, never as a crash or a silent fallback."""
+    import ctypes as C
+    from probabilisticsemslam_b200 import _lib
+    lib = _lib.lib()
+    pb = synth.g1_dense(4)
+    nr, nc = pb.num_row, pb.nM.astype(np.int32)
+    found = np.zeros(4, np.int32)
+    p = lambda a: a.ctypes.data
+    # numRow < numCol
+    bad_nr = nc.copy() - 1
+    rc = lib.pda_murty_batch_host(p(pb.costs), p(pb.cost_off), p(bad_nr), p(nc), 4, 5, 0, 0.0, 0, 0, None, None, None, None, None,
+                                  p(found), 0, None, None, None, 0)
+    assert rc == -1 and b"numRow" in lib.pda_last_error()
+    # k < 1
+    rc = lib.pda_murty_batch_host(p(pb.costs), p(pb.cost_off), p(nr), p(nc), 4, 0, 0, 0.0, 0, 0, None, None, None, None, None,
+                                  p(found), 0, None, None, None, 0)
+    assert rc == -1
+    # weights requested without outputs
+    rc = lib.pda_murty_batch_host(p(pb.costs), p(pb.cost_off), p(nr), p(nc), 4, 5, 1, 42.0, 0, 0, None, None, None, None, None,
+                                  p(found), 1, None, None, None, 0)
+    assert rc == -1
+    # dimension above PDA_MAX_DIM
+    big = synth.pack([np.zeros((200, 3))], [197])
+    rc = lib.pda_murty_batch_host(p(big.costs), p(big.cost_off), p(big.num_row), p(big.nM.astype(np.int32)), 1, 5, 0, 0.0, 0, 0,
+                                  None, None, None, None, None, p(found), 0, None, None, None, 0)
+    assert rc == -3
+    # device out of range
+    rc = lib.pda_murty_batch_host(p(pb.costs), p(pb.cost_off), p(nr), p(nc), 4, 5, 0, 0.0, 0, 0, None, None, None, None, None,
+                                  p(found), 0, None, None, None, 99)
+    assert rc == -1
+    # a workspace too small for a single arena
+    import torch
+    d = lambda t: t.data_ptr()
+    costs = torch.from_numpy(pb.costs).cuda(); off = torch.from_numpy(pb.cost_off).cuda()
+    tnr = torch.from_numpy(nr).cuda(); tnc = torch.from_numpy(nc).cuda(); tf = torch.zeros(4, dtype=torch.int32, device="cuda")
+    ws = torch.empty(1024, dtype=torch.uint8, device="cuda")
+    rc = lib.pda_murty_batch(d(costs), d(off), d(tnr), d(tnc), 4, 38, 8, 50, 0, 0.0, 0, 0, None, None, None, None, None, d(tf),
+                             0, None, None, None, d(ws), 1024, None)
+    assert rc == -4 and b"workspace" in lib.pda_last_error()
+    with pytest.raises(_lib.PdaError):
+        gpu_api.kBest2D(5, np.zeros((2, 3)))          # more columns than rows
