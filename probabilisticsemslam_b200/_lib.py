@@ -20,6 +20,7 @@ SIGNATURES = {
     "pda_device_count": (C.c_int, []),
     "pda_diag_dfma_tflops": (dbl, []),
     "pda_murty_workspace_bytes": (i64, [i64, i32, i32, i32]),
+    "pda_murty_set_path": (C.c_int, [i32]),
     "pda_murty_batch": (C.c_int, [ptr, ptr, ptr, ptr, i64, i32, i32, i32, i32, dbl, i32, i32,
                                   ptr, ptr, ptr, ptr, ptr, ptr, i32, ptr, ptr, ptr, ptr, i64, ptr]),
     "pda_murty_batch_host": (C.c_int, [ptr, ptr, ptr, ptr, i64, i32, i32, dbl, i32, i32,

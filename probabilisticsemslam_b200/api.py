@@ -26,6 +26,18 @@ WEIGHTS_NONE, WEIGHTS_GATED, WEIGHTS_UNGATED = 0, 1, 2
 GATE = 42.0  # assignment.cpp:9
 
 
+MURTY_PATHS = {"auto": 0, "warp": 1, "cta": 2}
+
+
+def set_murty_path(path: str) -> str:
+    """Which Murty kernel pda_murty_batch uses: "auto" (by batch size), "warp" (one warp per problem) or "cta" (one
+    CTA per problem wherever numCol <= 16).  Results are bit-identical; returns the previous setting."""
+    prev = lib().pda_murty_set_path(MURTY_PATHS[path])
+    if prev < 0:
+        check(prev)
+    return {v: k for k, v in MURTY_PATHS.items()}[prev]
+
+
 def _p(a):
     return None if a is None else a.ctypes.data
 

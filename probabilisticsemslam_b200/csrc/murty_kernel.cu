@@ -24,453 +24,10 @@
 // enumeration order are bit-identical to an IEEE-strict build of the reference.
 // The heap replays libstdc++'s __push_heap / __adjust_heap so that exact gain ties
 // pop in the same order as std::priority_queue<pMurtyHyp> (shortestPathCPP.cpp:30-42).
-#include "pda_internal.h"
-
-#include <math_constants.h>
+#include "murty_device.cuh"
 
 namespace pda {
 namespace {
-
-constexpr unsigned FULL = 0xffffffffu;
-
-// resident CTAs per SM the register allocator must leave room for (4 warps each)
-#ifndef PDA_MURTY_MINB
-#define PDA_MURTY_MINB 6
-#endif
-
-struct __align__(16) HeapEntry {
-    double gain;
-    int node;
-    int pad;
-};
-
-// ---- order-preserving 64-bit key for doubles ----------------------------------------------------
-__device__ __forceinline__ void to_key(double d, unsigned& khi, unsigned& klo) {
-    const unsigned hi = (unsigned)__double2hiint(d), lo = (unsigned)__double2loint(d);
-    const unsigned m = (unsigned)((int)hi >> 31);  // all ones for negatives
-    khi = hi ^ (m | 0x80000000u);
-    klo = lo ^ m;
-}
-__device__ __forceinline__ double from_key(unsigned khi, unsigned klo) {
-    const unsigned m = (khi & 0x80000000u) ? 0u : 0xffffffffu;
-    return __hiloint2double((int)(khi ^ (m | 0x80000000u)), (int)(klo ^ m));
-}
-constexpr unsigned KEY_INF_HI = 0xFFF00000u;  // key of +inf is (0xFFF00000, 0)
-
-__device__ __forceinline__ double warp_min(double x) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) { double y = __shfl_xor_sync(FULL, x, o); x = (y < x) ? y : x; }
-    return x;
-}
-__device__ __forceinline__ double warp_max(double x) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) { double y = __shfl_xor_sync(FULL, x, o); x = (x < y) ? y : x; }
-    return x;
-}
-
-// Per-warp view of shared memory.
-struct WarpSmem {
-    double* C;       // [ld * numCol] shifted cost matrix, real columns only
-    double* u;       // [32R] mirror of the working node's column duals
-    double* spc;     // [32R] shortestPathCost, published after a scan for the dual update
-    double* acc;     // [numCol * (nL+1)] weight accumulators
-    short* r4c;      // [32R] mirror of the working node's row4col
-    short* pred;     // [32R] predecessor column per row
-    unsigned short* c4r;  // [32R] mirror of the working node's col4row (0xffff = free)
-};
-
-// The working node, distributed over the warp.
-template <int R>
-struct Node {
-    double v[R];   // row duals           (lane owns rows  lane + 32 s)
-    double u[R];   // column duals        (lane owns cols  lane + 32 s)
-    int c4r[R];    // column of each owned row (-1 = free)
-    int r4c[R];    // row of each owned column (-1 = free)
-};
-
-// One relaxation pass of the row scan from column `cur` (shortestPathCPP.cpp:179-195 / 307-325).
-// Rows that must not take part carry v == -inf, which makes their reduced cost +inf, so no row mask is
-// needed: `t < cand` is simply never true for them.  REAL = the column exists in sm.C; otherwise it is
-// one of the reference's zero padding columns, C == +0.0 and delta + 0.0 == delta (delta is never -0.0:
-// the staged matrix holds no -0.0 and x - x rounds to +0.0).
-template <int R, bool REAL>
-__device__ __forceinline__ void relax(const double* __restrict__ Ccol, const int n, const double delta,
-                                      const double ucur, const double (&v)[R], const int cur,
-                                      double (&cand)[R], int (&pred)[R], const int lane) {
-    const double du = delta - ucur;  // used by the padding-column form only
-#pragma unroll
-    for (int s = 0; s < R; ++s) {
-        double t;
-        if (REAL) {
-            const double c = (lane + 32 * s < n) ? Ccol[lane + 32 * s] : 0.0;
-            t = ((delta + c) - ucur) - v[s];
-        } else {
-            t = du - v[s];
-        }
-        const bool better = t < cand[s];
-        cand[s] = better ? t : cand[s];
-        pred[s] = better ? cur : pred[s];
-    }
-}
-
-constexpr int NAN_HI = 0x7ff80000;  // high word of the NaN that marks a scanned row's candidate
-
-// Fast-forward over the reference's no-op hops.
-//
-// Most Dijkstra steps of a child solve (93 % on the benchmark shapes) go through rows that are paired with
-// zero-cost PADDING columns and change nothing: scanning such a column p from row r offers every other row
-// t = (cand[r] - u[p]) - v[row], which is not below what the row already holds, so the reference merely retires
-// r and moves to the next-closest row.  This routine proves that for a whole run of such rows at once and
-// retires them together, with results bit-identical to stepping through them:
-//   stopper  = the closest live row that is NOT paired with a padding column (a free row -- the sink -- or a row
-//              whose column has real costs); key order is (cand, row), the reference's first-minimum order
-//   F        = live rows paired with padding columns that come before the stopper in that order
-//   W        = min over F of fl(cand[r] - u[col(r)])   (what each of those hops would offer, before the row dual)
-//   test     : fl(W - v[row]) >= cand[row] for EVERY live row.  Rounding is monotone, so fl(W - v) is the smallest
-//              offer any hop of F could make to that row; if even that does not beat its candidate, no hop of F
-//              updates anything, in any order (a sufficient condition -- it also covers offers from hops that
-//              come after the row, which the reference never makes).
-// If the test passes every row of F is scanned at its current candidate (parked in sm.spc), predecessors stay as
-// they are, and the stopper is the next row to scan: (closest, delta) are returned so the caller skips its own
-// arg-min.  If it fails nothing is changed and the caller steps normally.  Returns 0 = not applied,
-// 1 = applied, 2 = applied and nothing finite is left (infeasible).
-template <int R>
-__device__ __forceinline__ int fast_forward(const int numColReal, const WarpSmem& sm, const Node<R>& nd,
-                                            const double (&vEff)[R], const double (&uRow)[R], double (&cand)[R],
-                                            int& closest, double& delta, const int lane) {
-    // the stopper
-    double sb = CUDART_INF;
-    int sbs = 0;
-#pragma unroll
-    for (int s = 0; s < R; ++s)
-        if (nd.c4r[s] < numColReal && cand[s] < sb) { sb = cand[s]; sbs = s; }
-    unsigned khi, klo;
-    to_key(sb, khi, klo);
-    const unsigned mhi = __reduce_min_sync(FULL, khi);
-    const unsigned mlo = __reduce_min_sync(FULL, (khi == mhi) ? klo : 0xffffffffu);
-    const bool win = (khi == mhi) && (klo == mlo);
-    const int rT = (int)__reduce_min_sync(FULL, win ? (unsigned)(lane + 32 * sbs) : 0xffffu);
-    const double kT = from_key(mhi, mlo);
-    // F and what its hops would offer
-    unsigned inF = 0u;
-    double wmin = CUDART_INF;
-    int nF = 0;
-#pragma unroll
-    for (int s = 0; s < R; ++s) {
-        const bool f = nd.c4r[s] >= numColReal && cand[s] < CUDART_INF &&
-                       (cand[s] < kT || (cand[s] == kT && lane + 32 * s < rT));
-        if (f) {
-            inF |= 1u << s;
-            const double w = cand[s] - uRow[s];
-            wmin = (w < wmin) ? w : wmin;
-        }
-        nF += __popc(__ballot_sync(FULL, f));
-    }
-    if (nF < 2) return 0;
-    to_key(wmin, khi, klo);
-    const unsigned whi = __reduce_min_sync(FULL, khi);
-    const unsigned wlo = __reduce_min_sync(FULL, (khi == whi) ? klo : 0xffffffffu);
-    const double W = from_key(whi, wlo);
-    bool beats = false;
-#pragma unroll
-    for (int s = 0; s < R; ++s) beats = beats || ((W - vEff[s]) < cand[s]);
-    if (__any_sync(FULL, beats)) return 0;
-#pragma unroll
-    for (int s = 0; s < R; ++s) {
-        if ((inF >> s) & 1u) {
-            sm.spc[lane + 32 * s] = cand[s];
-            cand[s] = __hiloint2double(NAN_HI, __double2loint(cand[s]));
-        }
-    }
-    closest = rT;
-    delta = kT;
-    return (mhi >= KEY_INF_HI) ? 2 : 1;
-}
-
-// One shortest augmenting path from `startCol` over the rows flagged in scanBits
-// (bit s = row lane+32s), then the dual update and the flip along the path.
-//   shortestPathCPP.cpp:168-226 / 297-356 (scan), :92-106 (duals), :108-116 (flip).
-// forbBits hides rows on the first hop only (:310).  numColReal = columns that exist in
-// sm.C; columns beyond are the reference's zero padding.  Returns true if infeasible.
-//
-// cand[s] is the reference's shortestPathCost of a row that is still to be scanned.  Rows outside the
-// scan set keep cand == +inf (their v is -inf, so they never relax); a row that HAS been scanned gets
-// its cand poisoned to NaN (one high-word write): `t < NaN` is false, so it never relaxes again, the
-// arg-min skips it, and "scanned" can be read back from it afterwards.  The cost at which a row was
-// scanned (== delta at that moment) is parked in sm.spc by lane 0, where the dual update reads it.
-template <int R>
-__device__ __forceinline__ bool augment_from(const int startCol, const int numColReal, const int ld,
-                                             const WarpSmem& sm, Node<R>& nd, const unsigned scanBits,
-                                             const unsigned forbBits, const int lane) {
-    double cand[R], vEff[R];
-    int pred[R];
-#pragma unroll
-    for (int s = 0; s < R; ++s) {
-        cand[s] = CUDART_INF;
-        pred[s] = 0;
-        vEff[s] = ((scanBits >> s) & 1u) ? nd.v[s] : -CUDART_INF;
-    }
-    int cur = startCol, sink;
-    double delta = 0.0;
-    {   // first hop: the forbidden rows sit this one out (:310)
-        double vHop[R];
-#pragma unroll
-        for (int s = 0; s < R; ++s) vHop[s] = ((forbBits >> s) & 1u) ? -CUDART_INF : vEff[s];
-        const double ucur = sm.u[cur];
-        if (cur < numColReal) relax<R, true>(sm.C + cur * ld, ld, delta, ucur, vHop, cur, cand, pred, lane);
-        else relax<R, false>(nullptr, ld, delta, ucur, vHop, cur, cand, pred, lane);
-    }
-    // u of the column each owned row is paired with (only rows paired with padding columns use it)
-    double uRow[R];
-#pragma unroll
-    for (int s = 0; s < R; ++s) uRow[s] = (nd.c4r[s] >= 0) ? sm.u[nd.c4r[s]] : 0.0;
-    bool padPrev = cur >= numColReal;  // the last relaxation came from a padding column
-    for (;;) {
-        int closest = 0;
-        int ff = 0;
-        if (padPrev) ff = fast_forward<R>(numColReal, sm, nd, vEff, uRow, cand, closest, delta, lane);
-        if (ff == 2) return true;
-        if (ff == 0) {
-            // lane-local first minimum (lower slot = lower row wins ties; NaN = already scanned), then the warp arg-min
-            double best = cand[0];
-            int bs = 0;
-#pragma unroll
-            for (int s = 1; s < R; ++s) if (cand[s] < best || best != best) { best = cand[s]; bs = s; }
-            unsigned khi, klo;
-            to_key(best, khi, klo);
-            const unsigned mhi = __reduce_min_sync(FULL, khi);
-            if (mhi >= KEY_INF_HI) return true;  // minVal == +inf (:197, :327): nothing finite is left
-            const unsigned mlo = __reduce_min_sync(FULL, (khi == mhi) ? klo : 0xffffffffu);
-            const bool win = (khi == mhi) && (klo == mlo);
-            closest = (int)__reduce_min_sync(FULL, win ? (unsigned)(lane + 32 * bs) : 0xffffu);
-            delta = from_key(mhi, mlo);
-        }
-        if (lane == 0) sm.spc[closest] = delta;
-#pragma unroll
-        for (int s = 0; s < R; ++s)
-            if (lane + 32 * s == closest) cand[s] = __hiloint2double(NAN_HI, __double2loint(cand[s]));
-        const unsigned next = sm.c4r[closest];
-        if (next == 0xffffu) { sink = closest; break; }
-        cur = (int)next;
-        padPrev = cur >= numColReal;
-        const double ucur = sm.u[cur];
-        if (padPrev) relax<R, false>(nullptr, ld, delta, ucur, vEff, cur, cand, pred, lane);
-        else relax<R, true>(sm.C + cur * ld, ld, delta, ucur, vEff, cur, cand, pred, lane);
-    }
-
-    // duals, using row4col as it was before the flip (:92-106).  A column other than startCol was scanned
-    // exactly when the row it is paired with was scanned (the sink row is unpaired).
-    unsigned rowsDone[R];
-#pragma unroll
-    for (int s = 0; s < R; ++s) {
-        rowsDone[s] = __ballot_sync(FULL, __double2hiint(cand[s]) == NAN_HI);
-        sm.pred[lane + 32 * s] = (short)pred[s];
-    }
-    __syncwarp();
-#pragma unroll
-    for (int s = 0; s < R; ++s) {
-        if ((rowsDone[s] >> lane) & 1u) nd.v[s] = (nd.v[s] - delta) + sm.spc[lane + 32 * s];
-        const int c = lane + 32 * s, r = nd.r4c[s];
-        bool seen = false;
-        if (r >= 0) {
-            unsigned w = rowsDone[0];
-#pragma unroll
-            for (int q = 1; q < R; ++q) if ((r >> 5) == q) w = rowsDone[q];
-            seen = (w >> (r & 31)) & 1u;
-        }
-        if (c == startCol) { nd.u[s] = nd.u[s] + delta; sm.u[c] = nd.u[s]; }
-        else if (seen) { nd.u[s] = (nd.u[s] + delta) - sm.spc[r]; sm.u[c] = nd.u[s]; }
-    }
-    // flip along the predecessor chain (:108-116); sm.r4c still holds the pre-flip pairing
-    int r = sink, c;
-    do {
-        c = sm.pred[r];
-        const int h = sm.r4c[c];
-#pragma unroll
-        for (int s = 0; s < R; ++s) {
-            if (lane + 32 * s == r) nd.c4r[s] = c;
-            if (lane + 32 * s == c) nd.r4c[s] = r;
-        }
-        r = h;
-    } while (c != startCol);
-    __syncwarp();
-#pragma unroll
-    for (int s = 0; s < R; ++s) {
-        sm.r4c[lane + 32 * s] = (short)nd.r4c[s];
-        sm.c4r[lane + 32 * s] = (unsigned short)nd.c4r[s];
-    }
-    __syncwarp();
-    return false;
-}
-
-// calcGain (:59-80): ascending column order, starting from 0.0.
-__device__ __forceinline__ double path_gain(const WarpSmem& sm, const int ld, const int numColGain) {
-    double g = 0.0;
-#pragma unroll 4
-    for (int c = 0; c < numColGain; ++c) g = g + sm.C[c * ld + sm.r4c[c]];
-    return g;
-}
-
-// ---- the heap: lane 0 only ----------------------------------------------------------------------------
-// Entries are 16 bytes and move as one 128-bit access.  The first `topCap` entries (the top levels, which every
-// pop walks through) live in the warp's shared memory, the rest in its global arena: a pop's sift-down is a chain
-// of dependent loads, and this turns most of its ~10 L2 round trips into shared-memory reads.
-struct Heap {
-    HeapEntry* top;   // shared memory, entries [0, topCap)
-    HeapEntry* deep;  // global arena, entry i at deep[i] (slots below topCap unused)
-    int topCap;
-    __device__ __forceinline__ HeapEntry get(int i) const { return (i < topCap) ? top[i] : deep[i]; }
-    __device__ __forceinline__ void put(int i, const HeapEntry& e) const {
-        if (i < topCap) top[i] = e; else deep[i] = e;
-    }
-};
-
-__device__ __forceinline__ void heap_sift_up(const Heap& h, int hole, const HeapEntry val) {
-    while (hole > 0) {
-        const int parent = (hole - 1) / 2;
-        const HeapEntry par = h.get(parent);
-        if (!(par.gain > val.gain)) break;
-        h.put(hole, par);
-        hole = parent;
-    }
-    h.put(hole, val);
-}
-__device__ __forceinline__ void heap_pop(const Heap& h, const int lenBefore) {
-    if (lenBefore > 1) {
-        const int len = lenBefore - 1;
-        const HeapEntry val = h.get(len);
-        int hole = 0, child = 0;
-        while (child < (len - 1) / 2) {
-            child = 2 * (child + 1);
-            const HeapEntry right = h.get(child), left = h.get(child - 1);  // both children in one round trip
-            const bool takeLeft = right.gain > left.gain;                     // right child wins an exact tie
-            if (takeLeft) child--;
-            h.put(hole, takeLeft ? left : right);
-            hole = child;
-        }
-        if ((len & 1) == 0 && child == (len - 2) / 2) {
-            child = 2 * (child + 1);
-            h.put(hole, h.get(child - 1));
-            hole = child - 1;
-        }
-        heap_sift_up(h, hole, val);
-    }
-}
-
-// ---- node arena -------------------------------------------------------------------------------------
-// layout of one stored node (D = geo.nodeDim):  v[D] | u[D] | c4r bytes[D] | r4c bytes[D] | forb words[R] | activeCol
-template <int R>
-__device__ __forceinline__ void node_store(unsigned char* base, const int D, const int n, const Node<R>& nd,
-                                           const unsigned forbBits, const int activeCol, const int lane) {
-    double* dv = reinterpret_cast<double*>(base);
-    unsigned char* bi = base + 16 * D;
-    unsigned* meta = reinterpret_cast<unsigned*>(base + 18 * D);
-#pragma unroll
-    for (int s = 0; s < R; ++s) {
-        const int i = lane + 32 * s;
-        if (i < n) {
-            dv[i] = nd.v[s];
-            dv[D + i] = nd.u[s];
-            bi[i] = (unsigned char)nd.c4r[s];
-            bi[D + i] = (unsigned char)nd.r4c[s];
-        }
-        const unsigned w = __ballot_sync(FULL, (forbBits >> s) & 1u);
-        if (lane == 0) meta[s] = w;
-    }
-    if (lane == 0) meta[R] = (unsigned)activeCol;
-}
-template <int R>
-__device__ __forceinline__ void node_load(const unsigned char* base, const int D, const int n, Node<R>& nd,
-                                          unsigned& forbBits, int& activeCol, const int lane) {
-    const double* dv = reinterpret_cast<const double*>(base);
-    const unsigned char* bi = base + 16 * D;
-    const unsigned* meta = reinterpret_cast<const unsigned*>(base + 18 * D);
-    forbBits = 0u;
-#pragma unroll
-    for (int s = 0; s < R; ++s) {
-        const int i = lane + 32 * s;
-        if (i < n) {
-            nd.v[s] = dv[i];
-            nd.u[s] = dv[D + i];
-            nd.c4r[s] = (int)(signed char)bi[i];
-            nd.r4c[s] = (int)(signed char)bi[D + i];
-        } else {
-            nd.v[s] = 0.0; nd.u[s] = 0.0; nd.c4r[s] = -1; nd.r4c[s] = -1;
-        }
-        forbBits |= ((meta[s] >> lane) & 1u) << s;
-    }
-    activeCol = (int)meta[R];
-}
-
-template <int R>
-__device__ __forceinline__ void publish_cols(const WarpSmem& sm, const Node<R>& nd, const int lane) {
-    __syncwarp();  // earlier readers of the mirrors (gain, new row) are done before they are overwritten
-#pragma unroll
-    for (int s = 0; s < R; ++s) {
-        sm.u[lane + 32 * s] = nd.u[s];
-        sm.r4c[lane + 32 * s] = (short)nd.r4c[s];
-        sm.c4r[lane + 32 * s] = (unsigned short)nd.c4r[s];
-    }
-    __syncwarp();
-}
-
-// makeCostMatrixSafe (:534-569): shift so every entry is >= 0; returns the shift.
-__device__ __forceinline__ double stage_safe_matrix(const double* Cg, double* Cs, const int numEl,
-                                                    const bool maximize, const bool makeSafe, const int lane) {
-    if (!makeSafe) {
-        for (int i = lane; i < numEl; i += 32) Cs[i] = Cg[i] + 0.0;  // + 0.0: no -0.0 in the staged matrix
-        __syncwarp();
-        return 0.0;
-    }
-    double d;
-    if (!maximize) {
-        d = CUDART_INF;
-        for (int i = lane; i < numEl; i += 32) { const double x = Cg[i]; d = (x < d) ? x : d; }
-        d = warp_min(d);
-        for (int i = lane; i < numEl; i += 32) Cs[i] = (Cg[i] - d) + 0.0;
-    } else {
-        d = -CUDART_INF;
-        for (int i = lane; i < numEl; i += 32) { const double x = Cg[i]; d = (d < x) ? x : d; }
-        d = warp_max(d);
-        for (int i = lane; i < numEl; i += 32) Cs[i] = (-Cg[i] + d) + 0.0;
-    }
-    __syncwarp();
-    return d;
-}
-
-template <int R>
-__device__ __forceinline__ void emit(const MurtyArgs& a, const long long p, const int slot, const int n, const int nc,
-                                     const Node<R>& nd, const double gainOut, const int lane) {
-    if (a.c4rBest) {
-        int64_t* o = a.c4rBest + a.c4rOff[p] + (int64_t)slot * n;
-#pragma unroll
-        for (int s = 0; s < R; ++s) if (lane + 32 * s < n) o[lane + 32 * s] = (int64_t)nd.c4r[s];
-    }
-    if (a.r4cBest) {
-        int64_t* o = a.r4cBest + a.r4cOff[p] + (int64_t)slot * nc;
-#pragma unroll
-        for (int s = 0; s < R; ++s) if (lane + 32 * s < nc) o[lane + 32 * s] = (int64_t)nd.r4c[s];
-    }
-    if (a.gainBest && lane == 0) a.gainBest[p * (long long)a.k + slot] = gainOut;
-}
-
-// assignmentProb / bruteForceProb accumulation of one hypothesis (assignment.cpp:620-640, 916-937)
-template <int R>
-__device__ __forceinline__ void add_weight(const MurtyArgs& a, const WarpSmem& sm, const Node<R>& nd, const int nc,
-                                           const int nL, const double best, const double gainOut, double& total,
-                                           const int lane) {
-    if (a.weightMode == PDA_WEIGHTS_GATED && !(best + a.weightGate > gainOut)) return;
-    const double w = exp(best - gainOut);
-    total += w;
-#pragma unroll
-    for (int s = 0; s < R; ++s) {
-        const int c = lane + 32 * s;
-        if (c < nc) {
-            const int to = nd.r4c[s] >= nL ? nL : nd.r4c[s];
-            sm.acc[c * (nL + 1) + to] += w;
-        }
-    }
-}
 
 template <int R>
 __device__ void solve_problem(const MurtyArgs& a, const long long p, const WarpSmem& sm, const Heap& heap,

@@ -7,6 +7,7 @@
 #include "pda_host_stage.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -111,6 +112,15 @@ static int64_t murty_full_warps(const MurtyGeometry& g, const DeviceInfo& dev) {
     return (int64_t)dev.smCount * g.ctasPerSm * g.warpsPerCta;
 }
 
+// Which kernel a batch goes to.  One CTA per problem (murty_cta_kernel.cu) is the latency path: it wins while the batch
+// is too small to give every SM ~4 problems' worth of warps, and loses beyond (it spends 16 warps on one problem).
+static std::atomic<int> g_murtyPath{PDA_MURTY_PATH_AUTO};
+static bool cta_eligible(int64_t nProblems, int32_t maxNumCol, const DeviceInfo& dev) {
+    const int path = g_murtyPath.load();
+    if (path == PDA_MURTY_PATH_WARP || maxNumCol > PDA_CTA_MAX_COL) return false;
+    return path == PDA_MURTY_PATH_CTA || nProblems <= 4LL * dev.smCount;
+}
+
 int64_t pda_murty_workspace_bytes(int64_t nProblems, int32_t k, int32_t maxNumRow, int32_t maxNumCol) {
     DeviceInfo dev;
     int rc = current_device_info(&dev);
@@ -119,7 +129,20 @@ int64_t pda_murty_workspace_bytes(int64_t nProblems, int32_t k, int32_t maxNumRo
     rc = murty_geometry(k, maxNumRow, maxNumCol, false, dev, &g);
     if (rc) return rc;
     int64_t warps = std::min<int64_t>(std::max<int64_t>(nProblems, 1), murty_full_warps(g, dev));
-    return 256 + warps * g.arenaStride + order_bytes(nProblems);
+    int64_t bytes = 256 + warps * g.arenaStride + order_bytes(nProblems);
+    if (cta_eligible(nProblems, maxNumCol, dev)) {
+        CtaGeometry cg;
+        if (murty_cta_geometry(k, maxNumRow, maxNumCol, false, dev, &g, &cg) == PDA_OK) {
+            const int64_t ctas = std::min<int64_t>(std::max<int64_t>(nProblems, 1), dev.smCount);
+            bytes = std::max<int64_t>(bytes, 256 + ctas * cg.arenaStride);
+        }
+    }
+    return bytes;
+}
+
+int pda_murty_set_path(int32_t path) {
+    if (path < PDA_MURTY_PATH_AUTO || path > PDA_MURTY_PATH_CTA) return fail(PDA_ERR_INVALID, "murty: bad path %d", path);
+    return g_murtyPath.exchange(path);
 }
 
 int pda_murty_batch(const double* costs, const int64_t* costOff, const int32_t* numRow, const int32_t* numCol,
@@ -141,14 +164,6 @@ int pda_murty_batch(const double* costs, const int64_t* costOff, const int32_t* 
     DeviceInfo dev;
     PDA_TRY(current_device_info(&dev));
     MurtyArgs a;
-    PDA_TRY(murty_geometry(k, maxNumRow, maxNumCol, weightMode != 0, dev, &a.geo));
-    int64_t warps = std::min<int64_t>(nProblems, murty_full_warps(a.geo, dev));
-    // the cost-ordered list goes behind the arenas when the workspace has room for it and there is a tail to shorten
-    const bool ordered = nProblems > 2 * warps && nProblems < (1LL << 31) &&
-                         workspaceBytes >= 256 + warps * a.geo.arenaStride + order_bytes(nProblems);
-    warps = std::min<int64_t>(warps, (workspaceBytes - 256 - (ordered ? order_bytes(nProblems) : 0)) / a.geo.arenaStride);
-    if (warps < 1) return fail(PDA_ERR_WORKSPACE, "murty: workspace of %lld B holds no arena (%lld B each)",
-                               (long long)workspaceBytes, (long long)a.geo.arenaStride);
     a.costs = costs; a.costOff = costOff; a.numRow = numRow; a.numCol = numCol; a.nProblems = nProblems;
     a.k = k; a.cutMode = cutMode; a.maximize = maximize; a.cutMaximize = cutMaximize; a.cutoff = cutoff;
     a.r4cBest = row4colBest; a.r4cOff = r4cOff; a.c4rBest = col4rowBest; a.c4rOff = c4rOff;
@@ -157,6 +172,27 @@ int pda_murty_batch(const double* costs, const int64_t* costOff, const int32_t* 
     a.probs = probs; a.probOff = probOff; a.nL = nL;
     a.cursor = reinterpret_cast<unsigned long long*>(workspace);
     a.arena = reinterpret_cast<unsigned char*>(workspace) + 256;
+    a.order = nullptr;
+    if (cta_eligible(nProblems, maxNumCol, dev)) {
+        const bool forced = g_murtyPath.load() == PDA_MURTY_PATH_CTA;
+        CtaGeometry cg;
+        int rc = murty_cta_geometry(k, maxNumRow, maxNumCol, weightMode != 0, dev, &a.geo, &cg);
+        const int64_t ctas = rc ? 0 : std::min<int64_t>(std::min<int64_t>(nProblems, dev.smCount), (workspaceBytes - 256) / cg.arenaStride);
+        if (rc == PDA_OK && ctas >= 1) {
+            a.nWarps = (int32_t)ctas;  // arenas == CTAs allowed to run
+            return launch_murty_cta(a, cg, reinterpret_cast<cudaStream_t>(stream));
+        }
+        if (forced) return rc ? rc : fail(PDA_ERR_WORKSPACE, "murty (CTA path): workspace of %lld B holds no arena (%lld B each)",
+                                          (long long)workspaceBytes, (long long)cg.arenaStride);
+    }
+    PDA_TRY(murty_geometry(k, maxNumRow, maxNumCol, weightMode != 0, dev, &a.geo));
+    int64_t warps = std::min<int64_t>(nProblems, murty_full_warps(a.geo, dev));
+    // the cost-ordered list goes behind the arenas when the workspace has room for it and there is a tail to shorten
+    const bool ordered = nProblems > 2 * warps && nProblems < (1LL << 31) &&
+                         workspaceBytes >= 256 + warps * a.geo.arenaStride + order_bytes(nProblems);
+    warps = std::min<int64_t>(warps, (workspaceBytes - 256 - (ordered ? order_bytes(nProblems) : 0)) / a.geo.arenaStride);
+    if (warps < 1) return fail(PDA_ERR_WORKSPACE, "murty: workspace of %lld B holds no arena (%lld B each)",
+                               (long long)workspaceBytes, (long long)a.geo.arenaStride);
     a.nWarps = (int32_t)warps;
     a.order = ordered ? reinterpret_cast<int32_t*>(a.arena + warps * a.geo.arenaStride) : nullptr;
     return launch_murty(a, reinterpret_cast<cudaStream_t>(stream));

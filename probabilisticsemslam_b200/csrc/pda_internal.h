@@ -62,6 +62,21 @@ struct MurtyArgs {
 };
 int launch_murty(const MurtyArgs& a, cudaStream_t stream);
 
+// ---- Murty k-best, one CTA per problem (murty_cta_kernel.cu): the latency path for small batches ----
+#define PDA_CTA_MAX_COL 16  // detections per problem the CTA path takes (children per split record)
+struct CtaGeometry {
+    int mirrorBytes;     // per-warp shared-memory mirrors (u, spc, r4c, pred, c4r)
+    int specSlack;       // arena slots that splits done ahead of their pop may hold
+    int maxNodes;
+    int64_t heapBytes;   // global part of the heap at the head of the arena
+    int64_t nodesOff;    // byte offset of the node slots inside the arena
+    int64_t arenaStride;
+    int ctlOff, heapTopOff, heapTopCap, smemBytes;
+};
+int murty_cta_geometry(int32_t k, int32_t maxNumRow, int32_t maxNumCol, bool weights, const DeviceInfo& dev,
+                       MurtyGeometry* g, CtaGeometry* cg);
+int launch_murty_cta(const MurtyArgs& a, const CtaGeometry& cg, cudaStream_t stream);
+
 struct LapArgs {
     const double* costs; const int64_t* costOff; const int32_t* numRow; const int32_t* numCol;
     const int32_t* numCol4Gain;

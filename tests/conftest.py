@@ -34,3 +34,12 @@ def gpu_api():
     from probabilisticsemslam_b200 import api, _lib
     assert _lib.lib().pda_device_count() > 0, "no CUDA device visible: -m gpu tests must run on the GPU box"
     return api
+
+
+@pytest.fixture(params=["warp", "cta"])
+def murty_path(request, gpu_api):
+    """Runs a test once per Murty kernel: one warp per problem (throughput) and one CTA per problem (latency).
+    Both must give the reference's bits; "cta" applies wherever numCol <= 16, the warp kernel takes the rest."""
+    prev = gpu_api.set_murty_path(request.param)
+    yield request.param
+    gpu_api.set_murty_path(prev)

@@ -7,7 +7,7 @@ import pytest
 from helpers import KBEST_FILES, assert_kbest_equal, bits, golden, kbest_cases
 from probabilisticsemslam_b200 import synth
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("murty_path")]
 
 
 def _run_cases(api, mats, k, use_cut, cutoff, maxi):
@@ -259,7 +259,8 @@ def test_c_abi_error_paths(gpu_api):
     assert rc == -1
     # dimension above PDA_MAX_DIM
     big = synth.pack([np.zeros((200, 3))], [197])
-    rc = lib.pda_murty_batch_host(p(big.costs), p(big.cost_off), p(big.num_row), p(big.nM.astype(np.int32)), 1, 5, 0, 0.0, 0, 0,
+    big_nr, big_nc = big.num_row, big.nM.astype(np.int32)  # keep the arrays alive across the call
+    rc = lib.pda_murty_batch_host(p(big.costs), p(big.cost_off), p(big_nr), p(big_nc), 1, 5, 0, 0.0, 0, 0,
                                   None, None, None, None, None, p(found), 0, None, None, None, 0)
     assert rc == -3
     # device out of range

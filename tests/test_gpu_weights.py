@@ -6,7 +6,7 @@ import pytest
 from helpers import bits, golden
 from probabilisticsemslam_b200 import synth
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("murty_path")]
 RTOL = 1e-9
 
 
