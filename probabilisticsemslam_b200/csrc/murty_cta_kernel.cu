@@ -24,12 +24,25 @@
 #include "murty_device.cuh"
 
 namespace pda {
+#ifdef PDA_CTA_PROFILE
+__device__ long long g_prof[16];
+#endif
 namespace {
 
 constexpr int CTA_WARPS = 16;
 constexpr int CTA_RECORDS = 64;             // split records (splits done but not yet committed)
-constexpr int CTA_MAXTASKS = 2 * CTA_WARPS;  // child solves per round
-constexpr int CTA_SPEC = 10;                 // nodes split per round, at most
+#ifndef PDA_CTA_MAXTASKS
+#define PDA_CTA_MAXTASKS 48
+#endif
+#ifndef PDA_CTA_SPEC
+#define PDA_CTA_SPEC 16
+#endif
+#ifndef PDA_CTA_AHEAD
+#define PDA_CTA_AHEAD 8
+#endif
+constexpr int CTA_MAXTASKS = PDA_CTA_MAXTASKS;  // child solves per round
+constexpr int CTA_SPEC = PDA_CTA_SPEC;         // nodes split per round, at most
+constexpr int CTA_AHEAD = PDA_CTA_AHEAD;       // no new picks while this many splits are waiting to be committed and the top is one of them
 
 struct Task {
     int parent;  // node whose split this child belongs to
@@ -42,8 +55,20 @@ struct CtaCtl {
     double CDelta, gain0Out, cutoffGain;
     unsigned long long freeRec;  // bit r set = record r is free
     long long problem;
-    int heapLen, sweep, nNodes, nTasks, done, nFound, nEmit, uncommitted, cutMax, cutting, feasible;
+    int heapLen, sweep, nNodes, nFound, nEmit, uncommitted, cutMax, cutting, feasible;
+    int nTasks[2];  // task list r&1 is executed in round r and was filled by warp 0 during round r-1
+    int done[2];    // done[r&1] is written by warp 0 during round r and read by everybody after that round's barrier
+    unsigned long long flight[2];  // flight[r&1]: records whose children are being solved during round r
+#ifdef PDA_CTA_PROFILE
+    long long tCommit, tSelect, tTasks, tRoot, tFinal, t0, ns0, tPop, tPush;
+    int rounds, tasksTotal, commits;
+#endif
 };
+#ifdef PDA_CTA_PROFILE
+#define PROF_T() clock64()
+#else
+#define PROF_T() 0LL
+#endif
 
 // HeapEntry::pad of this kernel: bits 0-7 activeCol, bits 8-23 split record + 1 (0 = not split yet)
 __device__ __forceinline__ int pad_active(int pad) { return pad & 0xff; }
@@ -55,7 +80,8 @@ struct CtaSmem {
     unsigned char* mirrors;  // CTA_WARPS x mirrorBytes
     double* recGain;         // [CTA_RECORDS][PDA_CTA_MAX_COL]
     int* recBase;            // [CTA_RECORDS]
-    Task* tasks;             // [CTA_MAXTASKS]
+    int* recRound;           // [CTA_RECORDS] round in which the record's children are solved
+    Task* tasks;             // [2][CTA_MAXTASKS]
     CtaCtl* ctl;
     HeapEntry* heapTop;
 };
@@ -67,7 +93,8 @@ __device__ __forceinline__ CtaSmem carve_cta(unsigned char* base, const MurtyGeo
     s.mirrors = reinterpret_cast<unsigned char*>(s.acc + g.pCap);
     s.recGain = reinterpret_cast<double*>(s.mirrors + (size_t)CTA_WARPS * cg.mirrorBytes);
     s.recBase = reinterpret_cast<int*>(s.recGain + CTA_RECORDS * PDA_CTA_MAX_COL);
-    s.tasks = reinterpret_cast<Task*>(s.recBase + CTA_RECORDS);
+    s.recRound = s.recBase + CTA_RECORDS;
+    s.tasks = reinterpret_cast<Task*>(s.recRound + CTA_RECORDS);
     s.ctl = reinterpret_cast<CtaCtl*>(base + cg.ctlOff);
     s.heapTop = reinterpret_cast<HeapEntry*>(base + cg.heapTopOff);
     return s;
@@ -107,6 +134,124 @@ __device__ __forceinline__ CtaArena carve_arena(unsigned char* base, const CtaGe
     return A;
 }
 
+// ---- the commit lane's heap ---------------------------------------------------------------------------
+// Same array, same libstdc++ moves as heap_pop / heap_sift_up in murty_device.cuh, tuned for ONE lane whose every
+// dependent load is exposed latency (the other 15 warps wait for it): entries move as one 128-bit access, gains
+// compare as integers (they are sums of entries of the shifted matrix, hence >= +0.0, where the bit pattern orders
+// like the value), and the sift-down looks two levels ahead -- the children and the four grandchildren come back
+// from one round trip to shared memory, which halves the chain of dependent loads of a pop.
+struct FastHeap {
+    int4* top;
+    int4* deep;
+    int topCap;
+    __device__ __forceinline__ int4 get(int i) const { return (i < topCap) ? top[i] : deep[i]; }
+    __device__ __forceinline__ void put(int i, const int4 e) const { if (i < topCap) top[i] = e; else deep[i] = e; }
+};
+__device__ __forceinline__ long long ekey(const int4 e) { return ((long long)e.y << 32) | (unsigned)e.x; }
+__device__ __forceinline__ int4 make_entry(double gain, int node, int pad) {
+    return make_int4(__double2loint(gain), __double2hiint(gain), node, pad);
+}
+__device__ __forceinline__ double entry_gain(const int4 e) { return __hiloint2double(e.y, e.x); }
+
+__device__ __forceinline__ void fast_sift_up(const FastHeap& h, int hole, const int4 val) {
+    const long long kv = ekey(val);
+    while (hole > 0) {
+        const int p1 = (hole - 1) / 2, p2 = (p1 - 1) / 2;  // p2 == 0 when p1 == 0 (C++ division truncates)
+        const int4 e1 = h.get(p1), e2 = h.get(p2);
+        if (!(ekey(e1) > kv)) break;
+        h.put(hole, e1);
+        hole = p1;
+        if (p1 == 0 || !(ekey(e2) > kv)) break;
+        h.put(hole, e2);
+        hole = p2;
+    }
+    h.put(hole, val);
+}
+__device__ __forceinline__ void fast_pop(const FastHeap& h, const int lenBefore) {
+    if (lenBefore <= 1) return;
+    const int len = lenBefore - 1;
+    const int4 val = h.get(len);
+    int hole = 0, child = 0;
+    while (4 * child + 6 < len) {  // both children of `child` have two children of their own: two levels per round trip
+        const int a = 2 * child + 1;
+        const int4 ea = h.get(a), eb = h.get(a + 1);
+        const int4 e0 = h.get(2 * a + 1), e1 = h.get(2 * a + 2), e2 = h.get(2 * a + 3), e3 = h.get(2 * a + 4);
+        const bool left1 = ekey(eb) > ekey(ea);  // the right child wins an exact tie
+        const int n1 = left1 ? a : a + 1;
+        const int4 gl = left1 ? e0 : e2, gr = left1 ? e1 : e3;
+        const bool left2 = ekey(gr) > ekey(gl);
+        const int n2 = 2 * n1 + (left2 ? 1 : 2);
+        h.put(hole, left1 ? ea : eb);
+        h.put(n1, left2 ? gl : gr);
+        hole = n2;
+        child = n2;
+    }
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        const int4 right = h.get(child), left = h.get(child - 1);
+        const bool takeLeft = ekey(right) > ekey(left);
+        if (takeLeft) child--;
+        h.put(hole, takeLeft ? left : right);
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        h.put(hole, h.get(child - 1));
+        hole = child - 1;
+    }
+    fast_sift_up(h, hole, val);
+}
+
+// The same two routines when the whole heap fits in shared memory (k = 200 and k = 1000 at 8 detections do): keys
+// are read as 64-bit loads, only indices are selected on, and an entry moves with one LDS.128 + STS.128 off the
+// dependent chain -- ~30 instructions per two levels instead of ~70, and the lane pays ~3.6 cycles per instruction.
+__device__ __forceinline__ long long skey(const int4* top, int i) { return reinterpret_cast<const long long*>(top)[2 * i]; }
+__device__ __forceinline__ void smem_sift_up(int4* top, int hole, const int4 val) {
+    const long long kv = ekey(val);
+    while (hole > 0) {
+        const int p1 = (hole - 1) / 2, p2 = (p1 - 1) / 2;
+        const long long k1 = skey(top, p1), k2 = skey(top, p2);
+        if (!(k1 > kv)) break;
+        top[hole] = top[p1];
+        hole = p1;
+        if (p1 == 0 || !(k2 > kv)) break;
+        top[hole] = top[p2];
+        hole = p2;
+    }
+    top[hole] = val;
+}
+__device__ __forceinline__ void smem_pop(int4* top, const int lenBefore) {
+    if (lenBefore <= 1) return;
+    const int len = lenBefore - 1;
+    const int4 val = top[len];
+    int hole = 0, child = 0;
+    while (4 * child + 6 < len) {
+        const int a = 2 * child + 1;
+        const long long ka = skey(top, a), kb = skey(top, a + 1);
+        const long long k0 = skey(top, 2 * a + 1), k1 = skey(top, 2 * a + 2), k2 = skey(top, 2 * a + 3), k3 = skey(top, 2 * a + 4);
+        const bool left1 = kb > ka;  // the right child wins an exact tie
+        const int n1 = left1 ? a : a + 1;
+        const long long gl = left1 ? k0 : k2, gr = left1 ? k1 : k3;
+        const int n2 = 2 * n1 + ((gr > gl) ? 1 : 2);
+        top[hole] = top[n1];
+        top[n1] = top[n2];
+        hole = n2;
+        child = n2;
+    }
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (skey(top, child) > skey(top, child - 1)) child--;
+        top[hole] = top[child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        top[hole] = top[child - 1];
+        hole = child - 1;
+    }
+    smem_sift_up(top, hole, val);
+}
+
 // ---- warp 0: staging, single-detection shortcut, root LAP (shortestPathCPP.cpp:119-238) ---------------
 template <int R>
 __device__ void root_phase(const MurtyArgs& a, const long long p, const CtaSmem& S, const WarpSmem& sm, const Heap& heap,
@@ -139,7 +284,7 @@ __device__ void root_phase(const MurtyArgs& a, const long long p, const CtaSmem&
     for (int s = 0; s < R; ++s) if (lane + 32 * s < n) allRows |= 1u << s;
     for (int c = 0; c < n; ++c) {
         if (augment_from<R>(c, nc, n, sm, nd, allRows, 0u, lane)) {
-            if (lane == 0) { a.nFound[p] = 0; ctl->feasible = 0; ctl->done = 1; ctl->nFound = 0; ctl->nEmit = 0; }
+            if (lane == 0) { a.nFound[p] = 0; ctl->feasible = 0; ctl->done[0] = ctl->done[1] = 1; ctl->nFound = 0; ctl->nEmit = 0; }
             if (wantW && nc > 1) {
                 double* out = a.probs + a.probOff[p];
                 for (int i = lane; i < nc * (nL + 1); i += 32) out[i] = CUDART_NAN;
@@ -173,106 +318,160 @@ __device__ void root_phase(const MurtyArgs& a, const long long p, const CtaSmem&
         ctl->CDelta = CDelta; ctl->gain0Out = gain0Out; ctl->cutoffGain = cutoffGain;
         ctl->cutMax = cutMax ? 1 : 0; ctl->cutting = a.cutMode != PDA_CUT_NONE;
         ctl->freeRec = ~0ULL;
-        ctl->heapLen = 1; ctl->sweep = 1; ctl->nNodes = 1; ctl->nTasks = 0; ctl->uncommitted = 0;
+        ctl->heapLen = 1; ctl->sweep = 1; ctl->nNodes = 1; ctl->nTasks[0] = ctl->nTasks[1] = 0; ctl->uncommitted = 0; ctl->flight[0] = ctl->flight[1] = 0ULL;
         ctl->feasible = 1;
-        ctl->done = (a.k <= 1) ? 1 : 0;
+        ctl->done[0] = ctl->done[1] = (a.k <= 1) ? 1 : 0;
         ctl->nFound = 1; ctl->nEmit = 1;
     }
 }
 
 // ---- warp 0, every round: commit in order, then choose the next splits -------------------------------
 __device__ void serial_phase(const MurtyArgs& a, const CtaGeometry& cg, const CtaSmem& S, const Heap& heap,
-                             const CtaArena& A, const int nc, const int lane) {
+                             const CtaArena& A, const int nc, const int round, const int lane) {
     CtaCtl* ctl = S.ctl;
+    const long long tc0 = PROF_T();
+    FastHeap fh;
+    fh.top = reinterpret_cast<int4*>(heap.top); fh.deep = reinterpret_cast<int4*>(heap.deep); fh.topCap = heap.topCap;
+    const bool allTop = cg.heapTopCap >= cg.maxNodes;
     if (lane == 0) {
         int heapLen = ctl->heapLen, sweep = ctl->sweep, uncommitted = ctl->uncommitted;
         unsigned long long freeRec = ctl->freeRec;
         const bool maximize = a.maximize != 0;
         const double CDelta = ctl->CDelta, gain0Out = ctl->gain0Out;
+        const unsigned long long flight = ctl->flight[round & 1];
         int done = 0;
+        int4 top = fh.get(0);
         while (sweep < a.k) {
-            const HeapEntry top = heap.get(0);
-            const int rec = pad_record(top.pad);
-            if (rec == 0) break;  // the top has not been split yet
-            const int a0 = pad_active(top.pad), cnt = nc - a0;
-            heap_pop(heap, heapLen);
+            const int rec = pad_record(top.w);
+            if (rec == 0 || ((flight >> (rec - 1)) & 1ULL)) break;  // the top is not split yet, or its children are being solved right now
+            const int a0 = pad_active(top.w), cnt = nc - a0;
+#ifdef PDA_CTA_PROFILE
+            const long long tp0 = PROF_T();
+#endif
+            if (allTop) smem_pop(fh.top, heapLen); else fast_pop(fh, heapLen);
             heapLen--;
+#ifdef PDA_CTA_PROFILE
+            const long long tp1 = PROF_T();
+            ctl->tPop += tp1 - tp0;
+#endif
             const int base = S.recBase[rec - 1];
             for (int j = 0; j < cnt; ++j) {  // children in column order (:493-522)
                 const double g = S.recGain[(rec - 1) * PDA_CTA_MAX_COL + j];
                 if (g == g) {
-                    HeapEntry e;
-                    e.gain = g; e.node = base + j; e.pad = a0 + j;
-                    heap_sift_up(heap, heapLen, e);
+                    if (allTop) smem_sift_up(fh.top, heapLen, make_entry(g, base + j, a0 + j));
+                    else fast_sift_up(fh, heapLen, make_entry(g, base + j, a0 + j));
                     heapLen++;
                 }
             }
+#ifdef PDA_CTA_PROFILE
+            ctl->tPush += PROF_T() - tp1;
+#endif
             freeRec |= 1ULL << (rec - 1);
             uncommitted -= cnt;
+#ifdef PDA_CTA_PROFILE
+            ctl->commits++;
+#endif
             if (heapLen == 0) { done = 1; ctl->nFound = sweep; ctl->nEmit = sweep; break; }
-            const HeapEntry nt = heap.get(0);  // hypothesis number `sweep` (:703-719)
+            const int4 nt = fh.get(0);  // hypothesis number `sweep` (:703-719)
+            const double ntGain = entry_gain(nt);
             double gainOut;
             bool stop = false;
             if (!maximize) {
-                gainOut = nt.gain + CDelta;
+                gainOut = ntGain + CDelta;
                 if (a.cutMode == PDA_CUT_RELATIVE && gainOut > gain0Out + a.cutoff) stop = true;
             } else {
-                gainOut = -nt.gain + CDelta;
+                gainOut = -ntGain + CDelta;
                 if (a.cutMode == PDA_CUT_RELATIVE && gainOut < gain0Out - a.cutoff) stop = true;
             }
-            A.orderNode[sweep] = nt.node;
+            A.orderNode[sweep] = nt.z;
             A.orderGain[sweep] = gainOut;
             if (stop) { done = 1; ctl->nFound = sweep; ctl->nEmit = sweep + 1; break; }
             sweep++;
+            top = nt;
         }
         if (!done && sweep >= a.k) { done = 1; ctl->nFound = sweep; ctl->nEmit = sweep; }
         ctl->heapLen = heapLen; ctl->sweep = sweep; ctl->uncommitted = uncommitted; ctl->freeRec = freeRec;
-        ctl->done = done;
+        ctl->done[round & 1] = done;
     }
     __syncwarp();
-    if (ctl->done) return;
+#ifdef PDA_CTA_PROFILE
+    const long long tc1 = PROF_T();
+    if (lane == 0) ctl->tCommit += tc1 - tc0;
+#endif
+    if (ctl->done[round & 1]) return;
 
-    // ---- choose what to split this round: the cheapest unsplit entries among the first 32 of the heap
+    // Picking costs this warp ~3 000 cycles and it is the critical path, so it is skipped while enough splits are
+    // already waiting (done or in flight) and the top of the heap is among them.
+    if (pad_record(heap.get(0).pad) != 0 && 64 - __popcll(ctl->freeRec) >= CTA_AHEAD) {
+        if (lane == 0) { ctl->flight[(round + 1) & 1] = 0ULL; ctl->nTasks[(round + 1) & 1] = 0; }
+        return;
+    }
+    // ---- choose what the workers split NEXT round: the cheapest unsplit entries among the first 32 of the heap.
+    // All lanes at once: every lane ranks its entry against the other 31 (gains order like their bit patterns), the
+    // lane of rank q then decides for the q-th cheapest; the limits are monotone in q, so "admitted" is a prefix.
     const int heapLen = ctl->heapLen;
     const int m = heapLen < 32 ? heapLen : 32;
     HeapEntry e;
     e.gain = CUDART_INF; e.node = 0; e.pad = 0;
     if (lane < m) e = heap.get(lane);
-    double key = (lane < m && pad_record(e.pad) == 0) ? e.gain : CUDART_INF;
-    unsigned long long freeRec = ctl->freeRec;
-    int nNodes = ctl->nNodes, uncommitted = ctl->uncommitted, nTasks = 0;
-    for (int it = 0; it < CTA_SPEC; ++it) {
-        unsigned khi, klo;
-        to_key(key, khi, klo);
-        const unsigned mhi = __reduce_min_sync(FULL, khi);
-        if (mhi >= KEY_INF_HI) break;
-        const unsigned mlo = __reduce_min_sync(FULL, (khi == mhi) ? klo : 0xffffffffu);
-        const bool win = (khi == mhi) && (klo == mlo);
-        const int j = (int)__reduce_min_sync(FULL, win ? (unsigned)lane : 0xffffu);
-        const int a0 = __shfl_sync(FULL, pad_active(e.pad), j);
-        const int parent = __shfl_sync(FULL, e.node, j);
-        const int cnt = nc - a0;
-        if (it > 0) {  // speculative: needs task room, a spare record (one stays reserved for a top) and arena slack
-            if (nTasks + cnt > CTA_MAXTASKS || __popcll(freeRec) < 2 || uncommitted + cnt > cg.specSlack) break;
-        }
-        const int rec = __ffsll((long long)freeRec) - 1;
-        freeRec &= ~(1ULL << rec);
-        if (lane == j) {
-            e.pad |= (rec + 1) << 8;
-            heap.put(j, e);
-            key = CUDART_INF;
-        }
-        if (lane < cnt) {
-            Task t;
-            t.parent = parent; t.child = nNodes + lane; t.c = (short)(a0 + lane); t.rec = (short)rec;
-            S.tasks[nTasks + lane] = t;
-        }
-        if (lane == 0) S.recBase[rec] = nNodes;
-        nNodes += cnt;
-        uncommitted += cnt;
-        nTasks += cnt;
+    const bool unsplit = lane < m && pad_record(e.pad) == 0;
+    const long long kk = unsplit ? __double_as_longlong(e.gain) : 0x7fffffffffffffffLL;
+    int rank = 0;
+#pragma unroll
+    for (int o = 0; o < 32; ++o) {
+        const long long ko = __shfl_sync(FULL, kk, o);
+        rank += (ko < kk || (ko == kk && o < lane)) ? 1 : 0;
     }
-    if (lane == 0) { ctl->freeRec = freeRec; ctl->nNodes = nNodes; ctl->uncommitted = uncommitted; ctl->nTasks = nTasks; }
+    unsigned char* inv = reinterpret_cast<unsigned char*>(S.tasks + 2 * CTA_MAXTASKS);  // 32 bytes of scratch behind the task lists
+    inv[rank] = (unsigned char)lane;
+    __syncwarp();
+    const int src = inv[lane];  // this lane now speaks for the entry of rank `lane`
+    const bool valid = __shfl_sync(FULL, unsplit ? 1 : 0, src) != 0;
+    const int a0 = __shfl_sync(FULL, pad_active(e.pad), src);
+    const int parent = __shfl_sync(FULL, e.node, src);
+    const int cnt = valid ? nc - a0 : 0;
+    int pre = cnt;  // inclusive prefix of children counts in rank order
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(FULL, pre, o);
+        if (lane >= o) pre += y;
+    }
+    const unsigned long long freeRec0 = ctl->freeRec;
+    const int nNodes0 = ctl->nNodes, uncommitted0 = ctl->uncommitted;
+    const bool mandatory = lane == 0 && src == 0;  // the heap top itself: always split (one record is kept back for it)
+    const bool admitted = valid && lane < CTA_SPEC &&
+                          (mandatory || (pre <= CTA_MAXTASKS && __popcll(freeRec0) - lane >= 2 && uncommitted0 + pre <= cg.specSlack));
+    const unsigned admMask = __ballot_sync(FULL, admitted);
+    // monotone limits => admMask is a run of low bits, except that a failed rank 0 blocks everything behind it
+    const int nAdm = (admMask & 1u) ? __ffs(~admMask) - 1 : 0;
+    unsigned long long fr = freeRec0;
+    for (int i = 0; i < lane && i < nAdm; ++i) fr &= fr - 1;  // drop the records taken by cheaper ranks
+    const int rec = __ffsll((long long)fr) - 1;
+    if (lane < nAdm) {
+        const int childBase = nNodes0 + pre - cnt;
+        if (src < heap.topCap) heap.top[src].pad |= (rec + 1) << 8; else heap.deep[src].pad |= (rec + 1) << 8;
+        S.recBase[rec] = childBase;
+        Task* list = S.tasks + ((round + 1) & 1) * CTA_MAXTASKS + (pre - cnt);
+        for (int c = 0; c < cnt; ++c) {
+            Task t;
+            t.parent = parent; t.child = childBase + c; t.c = (short)(a0 + c); t.rec = (short)rec;
+            list[c] = t;
+        }
+    }
+    const int total = nAdm > 0 ? __shfl_sync(FULL, pre, nAdm - 1) : 0;
+    const unsigned long long frAfter = __shfl_sync(FULL, fr & (fr - 1), nAdm > 0 ? nAdm - 1 : 0);
+    if (lane == 0) {
+        const unsigned long long freeRec = nAdm > 0 ? frAfter : freeRec0;
+        ctl->flight[(round + 1) & 1] = freeRec0 & ~freeRec;
+        ctl->freeRec = freeRec; ctl->nNodes = nNodes0 + total; ctl->uncommitted = uncommitted0 + total;
+        ctl->nTasks[(round + 1) & 1] = total;
+    }
+#ifdef PDA_CTA_PROFILE
+    const int nTasks = total;
+#endif
+#ifdef PDA_CTA_PROFILE
+    if (lane == 0) { ctl->tSelect += PROF_T() - tc1; ctl->rounds++; ctl->tasksTotal += nTasks; }
+#endif
 }
 
 // ---- any warp: one child of one split (shortestPathUpdateCPP, shortestPathCPP.cpp:240-365) -----------
@@ -337,20 +536,36 @@ __device__ void solve_problem_cta(const MurtyArgs& a, const CtaGeometry& cg, con
     heap.topCap = cg.heapTopCap;
     CtaCtl* ctl = S.ctl;
 
+#ifdef PDA_CTA_PROFILE
+    if (threadIdx.x == 0) { ctl->tCommit = ctl->tSelect = ctl->tTasks = ctl->tPop = ctl->tPush = 0; ctl->rounds = ctl->tasksTotal = ctl->commits = 0; ctl->t0 = PROF_T(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ctl->ns0)); }
+#endif
     if (warp == 0) root_phase<R>(a, p, S, sm, heap, A, lane);
     __syncthreads();
-    const bool feasible = ctl->feasible != 0, doneAtRoot = ctl->done != 0;
+#ifdef PDA_CTA_PROFILE
+    if (threadIdx.x == 0) ctl->tRoot = PROF_T() - ctl->t0;
+#endif
+    const bool feasible = ctl->feasible != 0, doneAtRoot = ctl->done[0] != 0;
     __syncthreads();  // everyone has read the root's verdict before warp 0 may change it
     if (!feasible) return;
 
-    while (!doneAtRoot) {
-        if (warp == 0) serial_phase(a, cg, S, heap, A, nc, lane);
+    // Rounds: warp 0 commits what earlier rounds solved and picks the next splits WHILE warps 1..15 solve the splits
+    // picked one round earlier; one barrier per round.  Round 0 only picks (the root's split).
+    for (int round = 0; !doneAtRoot; ++round) {
+        if (warp == 0) {
+            serial_phase(a, cg, S, heap, A, nc, round, lane);
+        } else {
+            const int nT = ctl->nTasks[round & 1];
+            const long long tt0 = PROF_T();
+            for (int t = warp - 1; t < nT; t += CTA_WARPS - 1)
+                run_task<R>(a, S, sm, A, S.tasks[(round & 1) * CTA_MAXTASKS + t], n, nc, lane);
+#ifdef PDA_CTA_PROFILE
+            if (threadIdx.x == 32) ctl->tTasks += PROF_T() - tt0;
+#endif
+        }
         __syncthreads();
-        if (ctl->done) break;  // uniform: ctl is only written by warp 0 between the second and the first barrier
-        const int nT = ctl->nTasks;
-        for (int t = warp; t < nT; t += CTA_WARPS) run_task<R>(a, S, sm, A, S.tasks[t], n, nc, lane);
-        __syncthreads();
+        if (ctl->done[round & 1]) break;
     }
+    const long long tf0 = PROF_T();
 
     // ---- lists (hpp:226-231) from the recorded pop order --------------------------------------------
     const int nFound = ctl->nFound, nEmit = ctl->nEmit;
@@ -393,6 +608,16 @@ __device__ void solve_problem_cta(const MurtyArgs& a, const CtaGeometry& cg, con
             a.probs[a.probOff[p] + t] = acc * (1.0 / total);
         }
     }
+#ifdef PDA_CTA_PROFILE
+    __syncthreads();
+    long long ns1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+    if (threadIdx.x == 0) {
+        g_prof[0] = ns1 - ctl->ns0; g_prof[1] = ctl->tRoot; g_prof[2] = ctl->tCommit; g_prof[3] = ctl->tSelect;
+        g_prof[4] = ctl->tTasks; g_prof[5] = PROF_T() - tf0; g_prof[6] = PROF_T() - ctl->t0; g_prof[7] = ctl->rounds;
+        g_prof[8] = ctl->tasksTotal; g_prof[9] = ctl->commits; g_prof[10] = ctl->tPop; g_prof[11] = ctl->tPush;
+    }
+#endif
 }
 
 template <int R>
@@ -433,14 +658,14 @@ int murty_cta_geometry(int32_t k, int32_t maxNumRow, int32_t maxNumCol, bool wei
     cg->nodesOff = (cg->heapBytes + orderBytes + 255) / 256 * 256;
     cg->arenaStride = (cg->nodesOff + nodes * g->nodeStride + 255) / 256 * 256;
     int off = 8 * (g->cCap + g->pCap) + CTA_WARPS * cg->mirrorBytes + 8 * CTA_RECORDS * PDA_CTA_MAX_COL +
-              4 * CTA_RECORDS + (int)sizeof(Task) * CTA_MAXTASKS;
+              8 * CTA_RECORDS + 2 * (int)sizeof(Task) * CTA_MAXTASKS + 32;
     off = round_up_i(off, 16);
     cg->ctlOff = off;
     off = round_up_i(off + (int)sizeof(CtaCtl), 16);
     cg->heapTopOff = off;
     int topCap = (dev.maxSmemOptin - off) / (int)sizeof(HeapEntry);
-    if (topCap > cg->maxNodes) topCap = cg->maxNodes;
     if (topCap < 32) return fail(PDA_ERR_UNSUPPORTED, "murty (CTA path): problem too large for shared memory");
+    if (topCap > cg->maxNodes) topCap = cg->maxNodes;
     cg->heapTopCap = topCap;
     cg->smemBytes = off + topCap * (int)sizeof(HeapEntry);
     return PDA_OK;
@@ -466,3 +691,9 @@ int launch_murty_cta(const MurtyArgs& a, const CtaGeometry& cg, cudaStream_t str
 }
 
 }  // namespace pda
+
+#ifdef PDA_CTA_PROFILE
+extern "C" int pda_debug_read_prof(long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, pda::g_prof, sizeof(long long) * 16);
+}
+#endif

@@ -51,6 +51,7 @@ int current_device_info(DeviceInfo* out) {
 std::mutex g_hostMu;
 std::vector<DevArena> g_arenas;
 std::vector<HostStreams> g_hostStreams;
+PinnedBuf g_pinned = {nullptr, 0};
 
 }  // namespace pda
 
@@ -230,6 +231,30 @@ int pda_murty_batch_host(const double* costs, const int64_t* costOff, const int3
     int64_t wsBytes = pda_murty_workspace_bytes(nProblems, k, maxR, maxC);
     if (wsBytes < 0) return (int)wsBytes;
     const size_t n = (size_t)nProblems;
+    const size_t ioBytes = 8 * (nCost + nR4c + nC4r + nProb + (gainBest ? n * (size_t)k : 0) + 4 * n) + 16 * n;
+    if (ioBytes <= PDA_PACKED_LIMIT) {  // small call: one pinned copy each way
+        Stage st(device);
+        PackedIO io(st);
+        const size_t oCost = io.in(costs, nCost * 8), oCostOff = io.in(costOff, n * 8), oNR = io.in(numRow, n * 4), oNC = io.in(numCol, n * 4);
+        const size_t oR4cOff = io.in(row4colBest ? r4cOff : nullptr, n * 8), oC4rOff = io.in(col4rowBest ? c4rOff : nullptr, n * 8);
+        const size_t oProbOff = io.in(weightMode ? probOff : nullptr, n * 8), oNL = io.in(weightMode ? nL : nullptr, n * 4);
+        const size_t oFound = io.out(nFound, n * 4), oGain = io.out(gainBest, gainBest ? n * (size_t)k * 8 : 0);
+        const size_t oProb = io.out(weightMode ? probs : nullptr, nProb * 8);
+        const size_t oR4c = io.out(row4colBest, nR4c * 8), oC4r = io.out(col4rowBest, nC4r * 8);
+        const size_t oWs = st.reserve((size_t)wsBytes);
+        PDA_TRY(st.commit());
+        HostStreams* hs = nullptr;
+        PDA_TRY(host_streams(device, &hs));
+        PDA_TRY(io.upload(hs->run));
+        PDA_TRY(pda_murty_batch(st.at<double>(oCost), st.at<int64_t>(oCostOff), st.at<int32_t>(oNR), st.at<int32_t>(oNC), nProblems,
+                                maxR, maxC, k, cutMode, cutoff, maximize, cutMaximize,
+                                row4colBest ? st.at<int64_t>(oR4c) : nullptr, st.at<int64_t>(oR4cOff),
+                                col4rowBest ? st.at<int64_t>(oC4r) : nullptr, st.at<int64_t>(oC4rOff),
+                                gainBest ? st.at<double>(oGain) : nullptr, st.at<int32_t>(oFound),
+                                weightMode, weightMode ? st.at<double>(oProb) : nullptr, st.at<int64_t>(oProbOff),
+                                st.at<int32_t>(oNL), st.at<unsigned char>(oWs), wsBytes, hs->run));
+        return io.download(hs->run);
+    }
     Stage st(device);
     const size_t oCost = st.reserve(nCost * 8), oCostOff = st.reserve(n * 8), oNR = st.reserve(n * 4), oNC = st.reserve(n * 4);
     const size_t oR4c = st.reserve(nR4c * 8), oR4cOff = st.reserve(n * 8), oC4r = st.reserve(nC4r * 8), oC4rOff = st.reserve(n * 8);

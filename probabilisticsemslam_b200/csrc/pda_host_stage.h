@@ -6,6 +6,7 @@
 
 #include "pda_internal.h"
 
+#include <cstring>
 #include <mutex>
 #include <vector>
 
@@ -84,6 +85,61 @@ template <class T> inline int d2h(T* dst, const T* src, size_t n, cudaStream_t s
     return PDA_OK;
 }
 #define PDA_TRY(expr) do { int _rc = (expr); if (_rc != PDA_OK) return _rc; } while (0)
+
+// Small calls (a batch of one from the C++ shims, a handful of window frames) are dominated by the fixed cost of each
+// cudaMemcpy from pageable memory (~10 us apiece, a dozen per call).  PackedIO lays all inputs out contiguously in the
+// device arena, then all outputs, mirrors that layout in ONE pinned host buffer, and moves each side with a single
+// asynchronous copy: reserve in()s, then out()s, then (after Stage::commit) upload() -> launches -> download().
+struct PinnedBuf { unsigned char* p; size_t cap; };
+extern PinnedBuf g_pinned;
+constexpr size_t PDA_PACKED_LIMIT = 8u << 20;  // bytes of inputs + outputs below which a *_host call takes this path
+
+class PackedIO {
+public:
+    explicit PackedIO(Stage& st) : st_(st), begin_(st.used()), inEnd_(st.used()), end_(st.used()) {}
+    size_t in(const void* src, size_t bytes) {
+        const size_t o = st_.reserve(bytes);
+        if (src && bytes) items_.push_back({o, const_cast<void*>(src), bytes, true});
+        inEnd_ = end_ = st_.used();
+        return o;
+    }
+    size_t out(void* dst, size_t bytes) {
+        const size_t o = st_.reserve(bytes);
+        if (dst && bytes) items_.push_back({o, dst, bytes, false});
+        end_ = st_.used();
+        return o;
+    }
+    size_t bytes() const { return end_ - begin_; }
+    int upload(cudaStream_t s) {
+        const size_t need = end_ - begin_;
+        if (g_pinned.cap < need) {
+            if (g_pinned.p) cudaFreeHost(g_pinned.p);
+            g_pinned.p = nullptr; g_pinned.cap = 0;
+            const size_t want = need + need / 2 + 4096;
+            PDA_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&g_pinned.p), want, cudaHostAllocDefault));
+            g_pinned.cap = want;
+        }
+        for (const Item& it : items_)
+            if (it.input) memcpy(g_pinned.p + (it.off - begin_), it.host, it.bytes);
+        if (inEnd_ > begin_)
+            PDA_CUDA_TRY(cudaMemcpyAsync(st_.at<unsigned char>(begin_), g_pinned.p, inEnd_ - begin_, cudaMemcpyHostToDevice, s));
+        return PDA_OK;
+    }
+    int download(cudaStream_t s) {
+        if (end_ > inEnd_)
+            PDA_CUDA_TRY(cudaMemcpyAsync(g_pinned.p + (inEnd_ - begin_), st_.at<unsigned char>(inEnd_), end_ - inEnd_,
+                                         cudaMemcpyDeviceToHost, s));
+        PDA_CUDA_TRY(cudaStreamSynchronize(s));
+        for (const Item& it : items_)
+            if (!it.input) memcpy(it.host, g_pinned.p + (it.off - begin_), it.bytes);
+        return PDA_OK;
+    }
+private:
+    struct Item { size_t off; void* host; size_t bytes; bool input; };
+    Stage& st_;
+    size_t begin_, inEnd_, end_;
+    std::vector<Item> items_;
+};
 
 }  // namespace pda
 #endif
