@@ -6,8 +6,9 @@
  * through libpda_b200.so; the *Batch forms underneath are what a multi-frame caller should use.
  *
  * Not here: the GTSAM / OpenCV typed entry points of the reference header (getAssignmentProbs, asgnBB,
- * computeQuadricCostMatrix, computeBBCostMatrix, getMeans, getCovs, saveAssignmentProb).  They only build
- * cost matrices and then call the functions below; keep the reference's definitions for them.
+ * computeBBCostMatrix, getMeans, getCovs, saveAssignmentProb).  They only unpack GTSAM / OpenCV objects and then call
+ * the functions below (the *Raw / *FromMoments forms take what they unpack); keep the reference's definitions for
+ * them.
  */
 #ifndef sensSLAM_assignment
 #define sensSLAM_assignment
@@ -37,6 +38,33 @@ void toProbs(std::vector<double>& costMatrix);
  * In the reference's getAssignmentProbs, replace lines :57-74 by a call to this. */
 std::vector<std::vector<double> > getAssignmentProbsFromCosts(const std::vector<double>& costMatrix, size_t nL, size_t nM,
                                                               size_t k, bool usePerm);
+
+/* computeQuadricCostMatrix (reference assignment.h:31-33, assignment.cpp:705-722) and getAssignmentProbs
+ * (assignment.h:11-13, assignment.cpp:38-74 with usePerm == 0) on raw moments: a mean is 3 doubles, a covariance 9
+ * (column-major 3x3 -- Eigen's layout, so &cov(0,0) of an Eigen::Matrix3d can be copied as is), landmarks first.
+ * nonassign = runConsts.NONASSIGN_QUADRIC, k = runConsts.k.  The second form never materialises the cost matrix on the
+ * host: moments go in, weights come out of one device pipeline. */
+std::vector<double> computeQuadricCostMatrixRaw(const std::vector<double>& landMeans, const std::vector<double>& landCovs,
+                                                const std::vector<double>& measMeans, const std::vector<double>& measCovs,
+                                                double nonassign);
+std::vector<std::vector<double> > getAssignmentProbsFromMoments(const std::vector<double>& landMeans,
+                                                                const std::vector<double>& landCovs,
+                                                                const std::vector<double>& measMeans,
+                                                                const std::vector<double>& measCovs, double nonassign, size_t k);
+#ifdef PDA_HAVE_EIGEN
+/* the reference's own argument types (m1/cov1 = landmarks, m2/cov2 = detections) */
+inline std::vector<double> computeQuadricCostMatrix(const std::vector<Eigen::Matrix<double, 3, 1> >& m1,
+                                                    const std::vector<Eigen::Matrix<double, 3, 3> >& cov1,
+                                                    const std::vector<Eigen::Vector3d>& m2,
+                                                    const std::vector<Eigen::Matrix<double, 3, 3> >& cov2, double nonassign) {
+    std::vector<double> a(3 * m1.size()), b(9 * cov1.size()), c(3 * m2.size()), d(9 * cov2.size());
+    for (size_t i = 0; i < m1.size(); i++) for (int j = 0; j < 3; j++) a[3 * i + j] = m1[i](j);
+    for (size_t i = 0; i < cov1.size(); i++) for (int j = 0; j < 9; j++) b[9 * i + j] = cov1[i].data()[j];
+    for (size_t i = 0; i < m2.size(); i++) for (int j = 0; j < 3; j++) c[3 * i + j] = m2[i](j);
+    for (size_t i = 0; i < cov2.size(); i++) for (int j = 0; j < 9; j++) d[9 * i + j] = cov2[i].data()[j];
+    return computeQuadricCostMatrixRaw(a, b, c, d, nonassign);
+}
+#endif
 
 /* asgnBB (reference assignment.h:21, assignment.cpp:724-775) on raw boxes: five doubles per box
  * (xmin, ymin, xmax, ymax, xOffset), nonassign = runConsts.NONASSIGN_BOUNDBOX.  Returns, per left box, the index of

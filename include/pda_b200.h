@@ -156,6 +156,35 @@ int pda_association_probs_batch_host(const double* costs, const int64_t* costOff
                                      int32_t device);
 
 /* ------------------------------------------------------------------------------------------
+ * The step in front of the path: cost matrices from quadric moments, on the device.
+ * pda_quadric_covs_batch: getCovs (assignment.cpp:693-703) -- quadrics = n 4x4 dual-quadric matrices (16 doubles
+ *   each; symmetric, so row- or column-major), covs = n 3x3 matrices (9 doubles each).
+ * pda_quadric_cost_batch: computeQuadricCostMatrix (assignment.cpp:705-722) for a batch of frames.  Frame f owns
+ *   landmarks [landOff[f], landOff[f+1]) and detections [measOff[f], measOff[f+1]) (offset arrays have nFrames+1
+ *   entries); a mean is 3 doubles (what getMeans returns, :685-692), a covariance 9 (column-major 3x3).  Writes the
+ *   (nL+nM) x nM column-major matrix of frame f at costs + costOff[f]: squared Mahalanobis distances
+ *   d^T (cov_l + cov_m)^-1 d (pivoted 3x3 LDLT as Eigen's ldlt().solve, :716-717), +inf, and `nonassign`
+ *   (NONASSIGN_QUADRIC) on the dummy diagonal.  nL / nM (may be NULL) receive the per-frame counts.
+ *   The _host form lays the matrices out back to back (costOff = prefix sums of (nL+nM)*nM).
+ * pda_association_from_moments_batch_host: getAssignmentProbs (assignment.cpp:38-74, usePerm == 0) from the moments
+ *   on -- cost matrices, conditionCosts, assignmentProb(k), weights back at the original landmark indices -- as one
+ *   device pipeline.  probs of frame f: nM x (nL+1) row-major, frames back to back.
+ * Eigen is not part of this library: the 3x3 solve restates Eigen 3.4's LDLT; agreement with the reference is to
+ * rounding (~1e-15 relative on SPD input), not bit-for-bit. */
+int pda_quadric_covs_batch(const double* quadrics, int64_t n, double* covs, void* stream);
+int pda_quadric_covs_batch_host(const double* quadrics, int64_t n, double* covs, int32_t device);
+int pda_quadric_cost_batch(const double* landMean, const double* landCov, const int64_t* landOff,
+                           const double* measMean, const double* measCov, const int64_t* measOff,
+                           int64_t nFrames, double nonassign, double* costs, const int64_t* costOff,
+                           int32_t* nL, int32_t* nM, void* stream);
+int pda_quadric_cost_batch_host(const double* landMean, const double* landCov, const int64_t* landOff,
+                                const double* measMean, const double* measCov, const int64_t* measOff,
+                                int64_t nFrames, double nonassign, double* costs, int32_t device);
+int pda_association_from_moments_batch_host(const double* landMean, const double* landCov, const int64_t* landOff,
+                                            const double* measMean, const double* measCov, const int64_t* measOff,
+                                            int64_t nFrames, double nonassign, int32_t k, double* probs, int32_t device);
+
+/* ------------------------------------------------------------------------------------------
  * Stereo bounding-box association: asgnBB (assignment.h:21, assignment.cpp:724-775) with computeBBCostMatrix
  * (:777-797) and boundBox::IoU (boundBox.h:62-75), for a batch of frames.  A box is five doubles
  * (xmin, ymin, xmax, ymax, xOffset); frame f owns left boxes [offL[f], offL[f+1]) and right boxes

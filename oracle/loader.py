@@ -46,6 +46,10 @@ class CpuChecker:
         f("permanent_batch", _dbl, [_ptr, _i64, _i64, _int, _ptr])
         f("bb_cost_matrix", None, [_ptr, C.c_long, _ptr, C.c_long, _dbl, _ptr])
         f("asgn_bb", None, [_ptr, C.c_long, _ptr, C.c_long, _dbl, _ptr])
+        if prefix == "orc":  # restatement only: needs Eigen on the reference side (oracle_quadric.c)
+            f("quadric_covs", None, [_ptr, _i64, _ptr])
+            f("quadric_cost_matrix", None, [_ptr, _ptr, _i64, _ptr, _ptr, _i64, _dbl, _ptr])
+            f("association_from_moments", _int, [_ptr, _ptr, _i64, _ptr, _ptr, _i64, _dbl, _i64, _ptr])
 
     def _fn(self, name, res, args):
         fn = getattr(self.lib, f"{self.prefix}_{name}")
@@ -175,6 +179,35 @@ class CpuChecker:
         out = np.full(max(bl.shape[0], 1), -7, np.int32)
         self._asgn_bb(_p(bl), bl.shape[0], _p(br), br.shape[0], float(nonassign), _p(out))
         return out[:bl.shape[0]]
+
+    # ---- cost matrices from quadric moments (restatement only) ---------------------------
+    def quadric_covs(self, quadrics):
+        q = np.ascontiguousarray(quadrics, np.float64).reshape(-1, 16)
+        out = np.zeros((q.shape[0], 9))
+        self._quadric_covs(_p(q), q.shape[0], _p(out))
+        return out.reshape(-1, 3, 3)
+
+    @staticmethod
+    def _moments(mean, cov):
+        m = np.ascontiguousarray(mean, np.float64).reshape(-1, 3)
+        c = np.ascontiguousarray(np.asarray(cov, np.float64).reshape(-1, 3, 3).transpose(0, 2, 1)).reshape(-1, 9)  # column-major 3x3
+        return m, c
+
+    def quadric_cost_matrix(self, land_mean, land_cov, meas_mean, meas_cov, nonassign):
+        lm, lc = self._moments(land_mean, land_cov)
+        mm, mc = self._moments(meas_mean, meas_cov)
+        nL, nM = lm.shape[0], mm.shape[0]
+        out = np.zeros((nL + nM) * nM)
+        self._quadric_cost_matrix(_p(lm), _p(lc), nL, _p(mm), _p(mc), nM, float(nonassign), _p(out))
+        return out.reshape((nL + nM, nM), order="F")
+
+    def association_from_moments(self, land_mean, land_cov, meas_mean, meas_cov, nonassign, k):
+        lm, lc = self._moments(land_mean, land_cov)
+        mm, mc = self._moments(meas_mean, meas_cov)
+        nL, nM = lm.shape[0], mm.shape[0]
+        out = np.zeros(max(nM * (nL + 1), 1))
+        self._association_from_moments(_p(lm), _p(lc), nL, _p(mm), _p(mc), nM, float(nonassign), int(k), _p(out))
+        return out[:nM * (nL + 1)].reshape(nM, nL + 1)
 
     # ---- batches (timing + bulk checks) ----------------------------------------------
     def batch(self, pb, k, *, cutoff=42.0, threads=1, want_probs=True, want_lists=True):

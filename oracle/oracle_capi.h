@@ -57,6 +57,14 @@ int orc_permanent_prob(const double* costs, int64_t nL, int64_t nM, int permOpt,
 /* assignment.cpp:57-74 (getAssignmentProbs after the cost matrix has been built). Returns 0, or 1 where the reference throws. */
 int orc_association_probs(const double* costs, int64_t nL, int64_t nM, int64_t k, int usePerm, double* probs);
 
+/* oracle_quadric.c: getCovs (assignment.cpp:693-703), computeQuadricCostMatrix (:705-722, the 3x3 Eigen LDLT solve
+ * restated -- parity unpinned, see that file), getAssignmentProbs from the moments on (:38-74).  No `ref_` twins. */
+void orc_quadric_covs(const double* Q, int64_t n, double* covs);
+void orc_quadric_cost_matrix(const double* landMean, const double* landCov, int64_t nL, const double* measMean,
+                             const double* measCov, int64_t nM, double nonassign, double* costs);
+int orc_association_from_moments(const double* landMean, const double* landCov, int64_t nL, const double* measMean,
+                                 const double* measCov, int64_t nM, double nonassign, int64_t k, double* probs);
+
 /* nwPerm.cpp:217-231 / 251-332 / 386-400; status 1 where the reference throws (dim > 32). */
 double orc_permanent_exact(const double* A, int64_t rows, int64_t cols, int* status);
 double orc_permanent_exact_square(const double* A, int64_t n, int* status);

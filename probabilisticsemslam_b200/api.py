@@ -192,6 +192,60 @@ def association_probs_batch(pb: ProblemBatch, k: int, device: int = 0) -> list[n
     return [probs[prob_off[p]:prob_off[p] + int(nM[p]) * (int(nL[p]) + 1)].reshape(int(nM[p]), int(nL[p]) + 1) for p in range(n)]
 
 
+def _pack_moments(frames):
+    """frames: list of (land_mean[nL,3], land_cov[nL,3,3], meas_mean[nM,3], meas_cov[nM,3,3]) -> flat arrays + offsets."""
+    lm = [np.asarray(f[0], np.float64).reshape(-1, 3) for f in frames]
+    mm = [np.asarray(f[2], np.float64).reshape(-1, 3) for f in frames]
+    col = lambda c: np.asarray(c, np.float64).reshape(-1, 3, 3).transpose(0, 2, 1).reshape(-1, 9)  # column-major 3x3
+    lc = [col(f[1]) for f in frames]
+    mc = [col(f[3]) for f in frames]
+    l_off = np.zeros(len(frames) + 1, np.int64); l_off[1:] = np.cumsum([a.shape[0] for a in lm])
+    m_off = np.zeros(len(frames) + 1, np.int64); m_off[1:] = np.cumsum([a.shape[0] for a in mm])
+    cat = lambda parts, w: np.ascontiguousarray(np.concatenate(parts, axis=0)) if parts else np.zeros((0, w))
+    return cat(lm, 3), cat(lc, 9), l_off, cat(mm, 3), cat(mc, 9), m_off
+
+
+def quadric_cost_batch(frames, nonassign: float, device: int = 0) -> list[np.ndarray]:
+    """computeQuadricCostMatrix (assignment.cpp:705-722) for a batch of frames -> list of (nL+nM, nM) matrices."""
+    lm, lc, lo, mm, mc, mo = _pack_moments(frames)
+    nL, nM = np.diff(lo), np.diff(mo)
+    sizes = (nL + nM) * nM
+    out = np.zeros(max(int(sizes.sum()), 1))
+    check(lib().pda_quadric_cost_batch_host(_p(lm), _p(lc), _p(lo), _p(mm), _p(mc), _p(mo), len(frames), float(nonassign), _p(out), device))
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    return [out[off[f]:off[f + 1]].reshape((int(nL[f] + nM[f]), int(nM[f])), order="F") for f in range(len(frames))]
+
+
+def association_from_moments_batch(frames, nonassign: float, k: int, device: int = 0) -> list[np.ndarray]:
+    """getAssignmentProbs (assignment.cpp:38-74, usePerm == 0) for a batch of frames, from the quadric moments on, as
+    one device pipeline -> list of (nM, nL+1) weight tables."""
+    lm, lc, lo, mm, mc, mo = _pack_moments(frames)
+    nL, nM = np.diff(lo), np.diff(mo)
+    sizes = nM * (nL + 1)
+    out = np.zeros(max(int(sizes.sum()), 1))
+    check(lib().pda_association_from_moments_batch_host(_p(lm), _p(lc), _p(lo), _p(mm), _p(mc), _p(mo), len(frames), float(nonassign),
+                                                        int(k), _p(out), device))
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    return [out[off[f]:off[f + 1]].reshape(int(nM[f]), int(nL[f]) + 1) for f in range(len(frames))]
+
+
+def computeQuadricCostMatrix(land_mean, land_cov, meas_mean, meas_cov, nonassign: float, device: int = 0) -> np.ndarray:
+    return quadric_cost_batch([(land_mean, land_cov, meas_mean, meas_cov)], nonassign, device)[0]
+
+
+def getCovs(quadrics: np.ndarray, device: int = 0) -> np.ndarray:
+    """getCovs (assignment.cpp:693-703): n 4x4 dual quadrics -> n 3x3 shape matrices."""
+    q = np.ascontiguousarray(quadrics, np.float64).reshape(-1, 16)
+    out = np.zeros((q.shape[0], 9))
+    check(lib().pda_quadric_covs_batch_host(_p(q), q.shape[0], _p(out), device))
+    return out.reshape(-1, 3, 3)
+
+
+def getAssignmentProbs(land_mean, land_cov, meas_mean, meas_cov, nonassign: float, k: int, device: int = 0) -> np.ndarray:
+    """The reference's SLAM entry point (assignment.cpp:38-74, usePerm == 0) on the moments getMeans/getCovs return."""
+    return association_from_moments_batch([(land_mean, land_cov, meas_mean, meas_cov)], nonassign, k, device)[0]
+
+
 def asgn_bb_batch(boxes_l: list[np.ndarray], boxes_r: list[np.ndarray], nonassign: float, device: int = 0) -> list[np.ndarray]:
     """asgnBB (assignment.cpp:724-775) for a batch of frames; boxes are [count, 5] = xmin, ymin, xmax, ymax, xOffset.
     Returns per frame the right-box index paired with each left box (-1 = none)."""

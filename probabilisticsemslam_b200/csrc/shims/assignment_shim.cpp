@@ -99,6 +99,35 @@ std::vector<std::vector<double> > getAssignmentProbsFromCosts(const std::vector<
     return probs;
 }
 
+std::vector<double> computeQuadricCostMatrixRaw(const std::vector<double>& landMeans, const std::vector<double>& landCovs,
+                                                const std::vector<double>& measMeans, const std::vector<double>& measCovs,
+                                                double nonassign) {
+    const size_t nL = landMeans.size() / 3, nM = measMeans.size() / 3;
+    if (landCovs.size() != 9 * nL || measCovs.size() != 9 * nM) throw std::runtime_error("computeQuadricCostMatrix: moment sizes disagree");
+    const int64_t offL[2] = {0, int64_t(nL)}, offM[2] = {0, int64_t(nM)};
+    std::vector<double> costs((nL + nM) * nM);
+    if (nM == 0) return costs;
+    pdaCheck(pda_quadric_cost_batch_host(landMeans.data(), landCovs.data(), offL, measMeans.data(), measCovs.data(), offM, 1, nonassign,
+                                         costs.data(), pdaShimDevice()),
+             "computeQuadricCostMatrix");
+    return costs;
+}
+
+std::vector<std::vector<double> > getAssignmentProbsFromMoments(const std::vector<double>& landMeans,
+                                                                const std::vector<double>& landCovs,
+                                                                const std::vector<double>& measMeans,
+                                                                const std::vector<double>& measCovs, double nonassign, size_t k) {
+    const size_t nL = landMeans.size() / 3, nM = measMeans.size() / 3;
+    if (landCovs.size() != 9 * nL || measCovs.size() != 9 * nM) throw std::runtime_error("getAssignmentProbs: moment sizes disagree");
+    if (nM == 0) return std::vector<std::vector<double> >();
+    const int64_t offL[2] = {0, int64_t(nL)}, offM[2] = {0, int64_t(nM)};
+    std::vector<double> probs(nM * (nL + 1), 0.0);
+    pdaCheck(pda_association_from_moments_batch_host(landMeans.data(), landCovs.data(), offL, measMeans.data(), measCovs.data(), offM, 1,
+                                                     nonassign, int32_t(k), probs.data(), pdaShimDevice()),
+             "getAssignmentProbsFromMoments");
+    return unflatten(probs, nM, nL + 1);
+}
+
 std::vector<int> asgnBBRaw(const std::vector<double>& boxesL, const std::vector<double>& boxesR, double nonassign) {
     const int64_t offL[2] = {0, int64_t(boxesL.size() / 5)}, offR[2] = {0, int64_t(boxesR.size() / 5)};
     std::vector<int32_t> a(size_t(offL[1]) ? size_t(offL[1]) : 1, -1);

@@ -158,6 +158,48 @@ def g2_gated(n: int, *, nL: int = 30, first: int = 0, seed: int = SEED + 1) -> P
     return pack(mats, [nL] * n)
 
 
+def quadric_frames(n: int, *, nL: int = 30, first: int = 0, seed: int = SEED + 4):
+    """Frames for the cost-matrix builder (computeQuadricCostMatrix, assignment.cpp:705-722): per frame ``nL`` landmark
+    quadrics scattered over a 100 m x 100 m x 4 m scene and 3-8 detected quadrics (a landmark plus ~0.7 m of noise
+    with probability 0.8, else clutter).  Every quadric is a centroid and a 3x3 shape matrix R diag(r^2) R^T with
+    radii 0.3-2.3 m and a random orientation.  Returns a list of (land_mean[nL,3], land_cov[nL,3,3],
+    meas_mean[nM,3], meas_cov[nM,3,3])."""
+    ids = np.arange(first, first + n, dtype=np.uint64)
+    per = 3 + 3 + 4  # centroid, radii, quaternion
+    x = stream(ids, 1 + per * (nL + 8) + 8 * 2, seed)
+    m = (np.uint64(3) + x[:, 0] % np.uint64(6)).astype(np.int32)
+    u = u01(x[:, 1:])
+
+    def shapes(v):  # v[..., 7] -> cov[..., 3, 3]
+        r2 = (0.3 + 2.0 * v[..., 0:3]) ** 2
+        q = v[..., 3:7] * 2.0 - 1.0 + 1e-3
+        q = q / np.linalg.norm(q, axis=-1, keepdims=True)
+        w, a, b, c = q[..., 0], q[..., 1], q[..., 2], q[..., 3]
+        R = np.stack([np.stack([1 - 2 * (b * b + c * c), 2 * (a * b - c * w), 2 * (a * c + b * w)], -1),
+                      np.stack([2 * (a * b + c * w), 1 - 2 * (a * a + c * c), 2 * (b * c - a * w)], -1),
+                      np.stack([2 * (a * c - b * w), 2 * (b * c + a * w), 1 - 2 * (a * a + b * b)], -1)], -2)
+        cov = np.einsum("...ij,...j,...kj->...ik", R, r2, R)
+        return 0.5 * (cov + np.swapaxes(cov, -1, -2))  # exactly symmetric, as getCovs builds it
+
+    frames = []
+    scale = np.array([100.0, 100.0, 4.0])
+    for p in range(n):
+        q = u[p, :per * (nL + 8)].reshape(nL + 8, per)
+        pick = u[p, per * (nL + 8):].reshape(8, 2)
+        land_mean = q[:nL, 0:3] * scale
+        land_cov = shapes(q[:nL, 3:10])
+        mm = int(m[p])
+        meas_mean = np.empty((mm, 3))
+        for c in range(mm):
+            if pick[c, 0] < 0.8 and nL > 0:
+                meas_mean[c] = land_mean[int(pick[c, 1] * nL) % nL] + (q[nL + c, 0:3] - 0.5) * 2.4
+            else:
+                meas_mean[c] = q[nL + c, 0:3] * scale
+        meas_cov = shapes(q[nL:nL + mm, 3:10])
+        frames.append((land_mean, land_cov, meas_mean, meas_cov))
+    return frames
+
+
 def dense_square(n_mats: int, dim: int, *, first: int = 0, seed: int = SEED + 2) -> np.ndarray:
     """Permanent inputs: ``n_mats`` dense dim x dim matrices, entries u01, column-major,
     returned as float64[n_mats, dim*dim]."""
