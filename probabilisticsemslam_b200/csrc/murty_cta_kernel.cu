@@ -460,6 +460,7 @@ __device__ void serial_phase(const MurtyArgs& a, const CtaGeometry& cg, const Ct
     }
     const int total = nAdm > 0 ? __shfl_sync(FULL, pre, nAdm - 1) : 0;
     const unsigned long long frAfter = __shfl_sync(FULL, fr & (fr - 1), nAdm > 0 ? nAdm - 1 : 0);
+    __syncwarp();  // every lane has read the counters before lane 0 replaces them
     if (lane == 0) {
         const unsigned long long freeRec = nAdm > 0 ? frAfter : freeRec0;
         ctl->flight[(round + 1) & 1] = freeRec0 & ~freeRec;

@@ -6,8 +6,13 @@ cat > /tmp/san_case.py <<'PY'
 import numpy as np
 from probabilisticsemslam_b200 import api, synth
 pb = synth.g1_dense(24, first=777)
-r = api.murty_batch(pb, 40, weight_mode=api.WEIGHTS_GATED)
-print("murty nFound", r.n_found[:6], float(r.probs.sum()))
+for path in ("warp", "cta"):
+    api.set_murty_path(path)
+    r = api.murty_batch(pb, 40, weight_mode=api.WEIGHTS_GATED)
+    print("murty", path, "nFound", r.n_found[:6], float(r.probs.sum()))
+api.set_murty_path("auto")
+fr = synth.quadric_frames(6, first=3)
+print("moments->weights", [float(t.sum()) for t in api.association_from_moments_batch(fr, 10.0, 40)])
 g2 = synth.g2_gated(6, first=5)
 cond, _ = api.condition_costs_batch(g2)
 keep = [p for p in range(len(cond)) if cond.matrix(p).shape[0] <= 14]
