@@ -488,28 +488,28 @@ __device__ void run_task(const MurtyArgs& a, const CtaSmem& S, const WarpSmem& s
     unsigned inPar = 0u;  // rows paired with columns >= c: columns a0..c-1 are fixed for this child (:506-508, 525-527)
 #pragma unroll
     for (int s = 0; s < R; ++s) if (lane + 32 * s < n && nd.c4r[s] >= c) inPar |= 1u << s;
-    publish_cols<R>(sm, nd, lane);
-    const int r0 = sm.r4c[c];
+    publish_cols<R>(sm, nd, lane);  // the parent's mirrors; the child solve leaves them alone
     unsigned hideFirst = 0u;
 #pragma unroll
     for (int s = 0; s < R; ++s) {
-        if (lane + 32 * s == r0) { nd.c4r[s] = -1; hideFirst |= 1u << s; }
+        if (nd.c4r[s] == c) {
+            nd.c4r[s] = -1; hideFirst |= 1u << s;
+            sm.c4r[lane + 32 * s] = 0xffffu;  // the freed row is the only sink of this search
+        }
         if (lane + 32 * s == c) nd.r4c[s] = -1;
     }
     if (c == a0) hideFirst = parForb;
-    if (lane == 0) sm.c4r[r0] = 0xffffu;
     __syncwarp();
     double result = CUDART_NAN;  // NaN = no child (infeasible or cut)
-    const bool infeasible = augment_from<R>(c, nc, n, sm, nd, inPar, hideFirst, lane);
+    const bool infeasible = augment_from<R, true>(c, nc, n, sm, nd, inPar, hideFirst, lane);
     if (!infeasible) {
-        const double g = path_gain(sm, n, nc);
+        const double g = path_gain_reg<R>(sm, nd, n, nc, lane);
         const double cutoffGain = S.ctl->cutoffGain;
         const bool cut = S.ctl->cutting && (S.ctl->cutMax ? (g < cutoffGain) : (g > cutoffGain));
         if (!cut) {
             unsigned childForb = hideFirst;
-            const int rNew = sm.r4c[c];
 #pragma unroll
-            for (int s = 0; s < R; ++s) if (lane + 32 * s == rNew) childForb |= 1u << s;
+            for (int s = 0; s < R; ++s) if (nd.c4r[s] == c) childForb |= 1u << s;
             node_store<R>(A.nodes + (size_t)t.child * a.geo.nodeStride, D, n, nd, childForb, c, lane);
             result = g;
         }

@@ -178,10 +178,15 @@ __device__ __forceinline__ int fast_forward(const int numColReal, const WarpSmem
 // its cand poisoned to NaN (one high-word write): `t < NaN` is false, so it never relaxes again, the
 // arg-min skips it, and "scanned" can be read back from it afterwards.  The cost at which a row was
 // scanned (== delta at that moment) is parked in sm.spc by lane 0, where the dual update reads it.
-template <int R>
+//
+// CHILD = a Murty child solve: the mirrors in shared memory hold the PARENT's u / row4col / col4row and are left
+// that way (the next child of the same split starts from the same parent), so the dual update and the flip touch the
+// registers only; uRowPar, when given, is the parent's "u of the column each row is paired with", computed once per
+// split (the freed row's entry is stale there, but a free row is a stopper and never consulted).
+template <int R, bool CHILD = false>
 __device__ __forceinline__ bool augment_from(const int startCol, const int numColReal, const int ld,
                                              const WarpSmem& sm, Node<R>& nd, const unsigned scanBits,
-                                             const unsigned forbBits, const int lane) {
+                                             const unsigned forbBits, const int lane, const double* uRowPar = nullptr) {
     double cand[R], vEff[R];
     int pred[R];
 #pragma unroll
@@ -203,7 +208,7 @@ __device__ __forceinline__ bool augment_from(const int startCol, const int numCo
     // u of the column each owned row is paired with (only rows paired with padding columns use it)
     double uRow[R];
 #pragma unroll
-    for (int s = 0; s < R; ++s) uRow[s] = (nd.c4r[s] >= 0) ? sm.u[nd.c4r[s]] : 0.0;
+    for (int s = 0; s < R; ++s) uRow[s] = uRowPar ? uRowPar[s] : ((nd.c4r[s] >= 0) ? sm.u[nd.c4r[s]] : 0.0);
     bool padPrev = cur >= numColReal;  // the last relaxation came from a padding column
     for (;;) {
         int closest = 0;
@@ -258,8 +263,8 @@ __device__ __forceinline__ bool augment_from(const int startCol, const int numCo
             for (int q = 1; q < R; ++q) if ((r >> 5) == q) w = rowsDone[q];
             seen = (w >> (r & 31)) & 1u;
         }
-        if (c == startCol) { nd.u[s] = nd.u[s] + delta; sm.u[c] = nd.u[s]; }
-        else if (seen) { nd.u[s] = (nd.u[s] + delta) - sm.spc[r]; sm.u[c] = nd.u[s]; }
+        if (c == startCol) { nd.u[s] = nd.u[s] + delta; if (!CHILD) sm.u[c] = nd.u[s]; }
+        else if (seen) { nd.u[s] = (nd.u[s] + delta) - sm.spc[r]; if (!CHILD) sm.u[c] = nd.u[s]; }
     }
     // flip along the predecessor chain (:108-116); sm.r4c still holds the pre-flip pairing
     int r = sink, c;
@@ -274,12 +279,14 @@ __device__ __forceinline__ bool augment_from(const int startCol, const int numCo
         r = h;
     } while (c != startCol);
     __syncwarp();
+    if (!CHILD) {
 #pragma unroll
-    for (int s = 0; s < R; ++s) {
-        sm.r4c[lane + 32 * s] = (short)nd.r4c[s];
-        sm.c4r[lane + 32 * s] = (unsigned short)nd.c4r[s];
+        for (int s = 0; s < R; ++s) {
+            sm.r4c[lane + 32 * s] = (short)nd.r4c[s];
+            sm.c4r[lane + 32 * s] = (unsigned short)nd.c4r[s];
+        }
+        __syncwarp();
     }
-    __syncwarp();
     return false;
 }
 
@@ -290,50 +297,87 @@ __device__ __forceinline__ double path_gain(const WarpSmem& sm, const int ld, co
     for (int c = 0; c < numColGain; ++c) g = g + sm.C[c * ld + sm.r4c[c]];
     return g;
 }
+// The same sum from the working node's registers: lane c fetches the one cost its column pays, then the terms are
+// added in the reference's order.  Lanes past the last column contribute +0.0, and g + 0.0 == g (g is a sum of
+// entries of the shifted matrix, never -0.0), so the chain runs over a fixed eight columns at a time with no
+// per-column branch: ~3 instructions per column instead of a dependent shared-memory walk by every lane.
+template <int R>
+__device__ __forceinline__ double path_gain_reg(const WarpSmem& sm, const Node<R>& nd, const int ld, const int numColGain,
+                                                const int lane) {
+    if (numColGain > 32) return path_gain(sm, ld, numColGain);
+    double x = 0.0;
+    if (lane < numColGain) x = sm.C[lane * ld + nd.r4c[0]];
+    double g = 0.0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) g = g + __shfl_sync(FULL, x, c);  // constant source lanes: SHFL with an immediate
+    for (int c0 = 8; c0 < numColGain; c0 += 8) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) g = g + __shfl_sync(FULL, x, (c0 + c) & 31);
+    }
+    return g;
+}
 
 // ---- the heap: lane 0 only ----------------------------------------------------------------------------
 // Entries are 16 bytes and move as one 128-bit access.  The first `topCap` entries (the top levels, which every
 // pop walks through) live in the warp's shared memory, the rest in its global arena: a pop's sift-down is a chain
-// of dependent loads, and this turns most of its ~10 L2 round trips into shared-memory reads.
+// of dependent loads, and this turns most of its ~10 L2 round trips into shared-memory reads.  Gains are compared
+// through their bit patterns: a gain is a sum of entries of the shifted matrix, i.e. >= +0.0 (never -0.0, never NaN),
+// and for such doubles the 64-bit integer order IS the numeric order -- two integer compares instead of an FP64 one.
 struct Heap {
     HeapEntry* top;   // shared memory, entries [0, topCap)
     HeapEntry* deep;  // global arena, entry i at deep[i] (slots below topCap unused)
     int topCap;
-    __device__ __forceinline__ HeapEntry get(int i) const { return (i < topCap) ? top[i] : deep[i]; }
+    __device__ __forceinline__ int4 get4(int i) const {
+        return (i < topCap) ? reinterpret_cast<const int4*>(top)[i] : reinterpret_cast<const int4*>(deep)[i];
+    }
+    __device__ __forceinline__ void put4(int i, const int4 e) const {
+        if (i < topCap) reinterpret_cast<int4*>(top)[i] = e; else reinterpret_cast<int4*>(deep)[i] = e;
+    }
+    __device__ __forceinline__ HeapEntry get(int i) const {
+        const int4 v = get4(i);
+        HeapEntry e;
+        e.gain = __hiloint2double(v.y, v.x); e.node = v.z; e.pad = v.w;
+        return e;
+    }
     __device__ __forceinline__ void put(int i, const HeapEntry& e) const {
-        if (i < topCap) top[i] = e; else deep[i] = e;
+        put4(i, make_int4(__double2loint(e.gain), __double2hiint(e.gain), e.node, e.pad));
     }
 };
+__device__ __forceinline__ long long heap_key(const int4 e) { return ((long long)e.y << 32) | (unsigned)e.x; }
 
-__device__ __forceinline__ void heap_sift_up(const Heap& h, int hole, const HeapEntry val) {
+__device__ __forceinline__ void heap_sift_up4(const Heap& h, int hole, const int4 val) {
+    const long long kv = heap_key(val);
     while (hole > 0) {
         const int parent = (hole - 1) / 2;
-        const HeapEntry par = h.get(parent);
-        if (!(par.gain > val.gain)) break;
-        h.put(hole, par);
+        const int4 par = h.get4(parent);
+        if (!(heap_key(par) > kv)) break;
+        h.put4(hole, par);
         hole = parent;
     }
-    h.put(hole, val);
+    h.put4(hole, val);
+}
+__device__ __forceinline__ void heap_sift_up(const Heap& h, int hole, const HeapEntry val) {
+    heap_sift_up4(h, hole, make_int4(__double2loint(val.gain), __double2hiint(val.gain), val.node, val.pad));
 }
 __device__ __forceinline__ void heap_pop(const Heap& h, const int lenBefore) {
     if (lenBefore > 1) {
         const int len = lenBefore - 1;
-        const HeapEntry val = h.get(len);
+        const int4 val = h.get4(len);
         int hole = 0, child = 0;
         while (child < (len - 1) / 2) {
             child = 2 * (child + 1);
-            const HeapEntry right = h.get(child), left = h.get(child - 1);  // both children in one round trip
-            const bool takeLeft = right.gain > left.gain;                     // right child wins an exact tie
+            const int4 right = h.get4(child), left = h.get4(child - 1);  // both children in one round trip
+            const bool takeLeft = heap_key(right) > heap_key(left);      // right child wins an exact tie
             if (takeLeft) child--;
-            h.put(hole, takeLeft ? left : right);
+            h.put4(hole, takeLeft ? left : right);
             hole = child;
         }
         if ((len & 1) == 0 && child == (len - 2) / 2) {
             child = 2 * (child + 1);
-            h.put(hole, h.get(child - 1));
+            h.put4(hole, h.get4(child - 1));
             hole = child - 1;
         }
-        heap_sift_up(h, hole, val);
+        heap_sift_up4(h, hole, val);
     }
 }
 

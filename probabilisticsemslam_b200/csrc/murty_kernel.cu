@@ -115,31 +115,37 @@ __device__ void solve_problem(const MurtyArgs& a, const long long p, const WarpS
         Node<R> par = nd;
         const unsigned parForb = forb;
         const int a0 = activeCol;
+        publish_cols<R>(sm, par, lane);  // the mirrors hold the parent for the whole split
         unsigned inPar = 0u;  // Row2ScanParent: rows paired with columns >= a0
+        double uRowPar[R];    // u of the column each row is paired with (fast_forward), the same for every child
 #pragma unroll
-        for (int s = 0; s < R; ++s) if (lane + 32 * s < n && par.c4r[s] >= a0) inPar |= 1u << s;
+        for (int s = 0; s < R; ++s) {
+            if (lane + 32 * s < n && par.c4r[s] >= a0) inPar |= 1u << s;
+            uRowPar[s] = (par.c4r[s] >= 0) ? sm.u[par.c4r[s]] : 0.0;
+        }
         for (int c = a0; c < nc; ++c) {
             nd = par;
-            publish_cols<R>(sm, nd, lane);
-            const int r0 = sm.r4c[c];  // the pairing this child must give up
-            unsigned hideFirst = 0u;
+            unsigned hideFirst = 0u, mine = 0u;  // mine: this lane owns the row that column c gives up
 #pragma unroll
             for (int s = 0; s < R; ++s) {
-                if (lane + 32 * s == r0) { nd.c4r[s] = -1; hideFirst |= 1u << s; }
+                if (par.c4r[s] == c) {
+                    nd.c4r[s] = -1; mine |= 1u << s;
+                    sm.c4r[lane + 32 * s] = 0xffffu;  // the freed row is the only sink of this search
+                }
                 if (lane + 32 * s == c) nd.r4c[s] = -1;
             }
-            if (c == a0) hideFirst = parForb;  // first child inherits every constraint on the active column (:490)
-            if (lane == 0) sm.c4r[r0] = 0xffffu;  // the freed row is the only sink of this search
+            hideFirst = (c == a0) ? parForb : mine;  // first child inherits every constraint on the active column (:490)
             __syncwarp();
-            const bool infeasible = augment_from<R>(c, nc, n, sm, nd, inPar, hideFirst, lane);
+            const bool infeasible = augment_from<R, true>(c, nc, n, sm, nd, inPar, hideFirst, lane, uRowPar);
+#pragma unroll
+            for (int s = 0; s < R; ++s) if ((mine >> s) & 1u) sm.c4r[lane + 32 * s] = (unsigned short)c;  // the parent's pairing again
             if (!infeasible) {
-                const double g = path_gain(sm, n, nc);
+                const double g = path_gain_reg<R>(sm, nd, n, nc, lane);
                 const bool cut = cutting && (cutMax ? (g < cutoffGain) : (g > cutoffGain));
                 if (!cut) {
                     unsigned childForb = hideFirst;
-                    const int rNew = sm.r4c[c];
 #pragma unroll
-                    for (int s = 0; s < R; ++s) if (lane + 32 * s == rNew) childForb |= 1u << s;
+                    for (int s = 0; s < R; ++s) if (nd.c4r[s] == c) childForb |= 1u << s;  // the row column c ended up with (:362)
                     node_store<R>(nodes + (size_t)nNodes * a.geo.nodeStride, D, n, nd, childForb, c, lane);
                     if (lane == 0) {
                         HeapEntry e;
@@ -150,8 +156,7 @@ __device__ void solve_problem(const MurtyArgs& a, const long long p, const WarpS
                     nNodes++;
                 }
             }
-#pragma unroll
-            for (int s = 0; s < R; ++s) if (lane + 32 * s == r0) inPar &= ~(1u << s);  // column c is fixed from here on
+            inPar &= ~mine;  // column c is fixed from here on
         }
         __syncwarp();
         if (heapLen == 0) break;
@@ -321,8 +326,8 @@ int murty_geometry(int32_t k, int32_t maxNumRow, int32_t maxNumCol, bool weights
     g->cCap = round_up(maxNumRow * maxNumCol, 2);
     g->pCap = weights ? round_up(maxNumCol * maxNumRow, 2) : 0;
     const int baseSmem = round_up(8 * (g->cCap + g->pCap + 2 * D) + 3 * 2 * D, 16);
-    // leftover shared memory (at the 24 warps per SM the register budget allows) holds the top of the heap
-    const int budget = (227 * 1024 - 6 * 1024) / 24;
+    // leftover shared memory (at the warps per SM the register budget allows) holds the top of the heap
+    const int budget = (227 * 1024 - PDA_MURTY_MINB * 1024) / (4 * PDA_MURTY_MINB);
     int topCap = budget > baseSmem ? (budget - baseSmem) / (int)sizeof(HeapEntry) : 0;
     if (topCap > g->maxNodes) topCap = g->maxNodes;
     if (topCap < 3) topCap = 0;
