@@ -299,6 +299,39 @@ def main():
     perm28_ms = float(t.item())
     perm28_value = shard.combine_partials(parts.cpu().numpy(), 28)
 
+    # ---- configs[0]: ONE 5x30 problem, k = 200, through the host call (the per-frame shape of the SLAM loop): the
+    #      batch-of-one goes to the one-CTA-per-problem kernel; H2D, launch and D2H are inside the wall-clock time
+    from probabilisticsemslam_b200 import api
+    C1 = synth.g1_dense(1, nM=5).matrix(0)
+    lat = {}
+    if rank == 0:
+        for path in ("cta", "warp"):
+            api.set_murty_path(path)
+            for _ in range(5):
+                api.assignmentProb(C1, 30, k)
+            ts = []
+            for _ in range(30):
+                t0 = time.perf_counter(); api.assignmentProb(C1, 30, k); ts.append(time.perf_counter() - t0)
+            lat[path] = 1e6 * statistics.median(ts)
+        api.set_murty_path("auto")
+    # ---- "next" row: moments in, weights out (cost matrices built on the device), 20 000 gated frames ------------
+    mom = None
+    if rank == 0:
+        frames = synth.quadric_frames(2000, first=123)
+        packed = api._pack_moments(frames * 10)
+        nLs, nMs = np.diff(packed[2]), np.diff(packed[5])
+        out = np.zeros(int((nMs * (nLs + 1)).sum()))
+        def mom_step():
+            _lib.check(lib.pda_association_from_moments_batch_host(*[a.ctypes.data for a in packed[:6]], len(nLs), 10.0, k,
+                                                                   out.ctypes.data, local))
+        mom_step()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            mom_step()
+        mom = {"frames": int(len(nLs)), "frames_per_s": 3 * len(nLs) / (time.perf_counter() - t0),
+               "call": "pda_association_from_moments_batch_host: quadric moments in (host), weights out (host); "
+                       "cost matrices, conditioning, k-best weights and un-compaction on the device"}
+
     fp64_peak = None
     if hasattr(lib, "pda_diag_dfma_tflops"):
         import ctypes as C
@@ -328,7 +361,7 @@ def main():
                         "(the bytes below cross the bus inside the timed region, overlapped with computing); e2e can exceed "
                         "`value` because the device-resident pass additionally writes the 7 GB of k-best lists",
                 "matches_device_run": e2e_matches},
-        "gpu_launches": 2 * args.steps,  # per step: order_by_cost_kernel + murty_kernel<2>
+        "gpu_launches": 2 * args.steps,  # per timed step: order_by_cost_kernel + murty_kernel<2>
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
                      "traffic": measured_traffic(n, k), "peak_source": pk_kind, "kernel": "murty_kernel<2>", "kernel_ms": kernel_ms,
                      "algorithmic_bytes_per_launch": alg_bytes,
@@ -338,6 +371,9 @@ def main():
         "extra": {"permanent_n24": {"gpu_ms": perm_ms, "unit": "ms", "flops": pplan.flops(),
                                     "achieved_tflops": pplan.flops() / (perm_ms * 1e-3) / 1e12,
                                     "fp64_peak_tflops_measured": fp64_peak},
+                  "config0_single_5x30_k200": {"host_call_us_cta_kernel": lat.get("cta"), "host_call_us_warp_kernel": lat.get("warp"),
+                                               "call": "assignmentProb, batch of one, host buffers (H2D + launch + D2H inside)"},
+                  "moments_to_weights": mom,
                   "permanent_n28_sharded": {"ms": perm28_ms, "ranks": world, "value": perm28_value,
                                             "exchange": "all_gather of 16-byte (hi, lo) partials, summed in rank order" if world > 1 else "none",
                                             "achieved_tflops": 3.0 * 28 * 2.0 ** 27 / (perm28_ms * 1e-3) / 1e12}},
@@ -351,6 +387,10 @@ def main():
         line["cpu_baseline"] = {"value": cpu_pps, "unit": UNIT, "cores": cores, "kind": kind,
                                 "sample": f"first {sample} problems of the same batch, {cores} threads, {what}; single thread: {one_pps:.0f} problems/s"}
         line["extra"]["permanent_n24"]["cpu_ms"] = cpu_permanent_ms(chk)
+        tc = []
+        for _ in range(10):
+            t0 = time.perf_counter(); chk.assignment_prob(C1, 30, k); tc.append(time.perf_counter() - t0)
+        line["extra"]["config0_single_5x30_k200"]["cpu_us"] = 1e6 * statistics.median(tc)
         # algorithmic work of the reference's formulation, counted by the oracle on a sample
         try:
             import ctypes as C

@@ -118,3 +118,27 @@ def test_stereo_box_association(gpu_api, oracle):
         matched += int((want >= 0).sum())
     assert matched > 1000
     np.testing.assert_array_equal(gpu_api.asgnBB(L[3], R[3], 0.2), oracle.asgn_bb(L[3], R[3], 0.2))
+
+
+def test_page_locked_buffers_are_used_in_place(gpu_api, oracle):
+    """pda_murty_batch_host with page-locked cost / weight buffers (the kernel reads and writes them over PCIe itself)
+    must give exactly what the staged path gives with pageable buffers."""
+    import torch
+    from probabilisticsemslam_b200 import _lib
+    lib = _lib.lib()
+    pb = synth.g1_dense(6000, first=70_000)   # ~23 MB of inputs + outputs: beyond the packed small-call path
+    k = 60
+    staged = gpu_api.assignment_prob_batch(pb, k)
+    n = len(pb)
+    nr, nc, nl = pb.num_row, pb.nM.astype(np.int32), pb.nL.astype(np.int32)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_costs, h_probs = pin(pb.costs), torch.zeros(staged.probs.shape[0], dtype=torch.float64).pin_memory()
+    found = np.zeros(n, np.int32)
+    p = lambda a: a.ctypes.data
+    _lib.check(lib.pda_murty_batch_host(h_costs.data_ptr(), p(pb.cost_off), p(nr), p(nc), n, k, 1, 42.0, 0, 0,
+                                        None, None, None, None, None, p(found), 1, h_probs.data_ptr(), p(staged.prob_off), p(nl), 0))
+    np.testing.assert_array_equal(found, staged.n_found)
+    np.testing.assert_array_equal(h_probs.numpy().view(np.int64), staged.probs.view(np.int64))
+    sub = pb.slice(0, 40)
+    want = oracle.batch(sub, k, threads=4, want_lists=False)
+    np.testing.assert_allclose(h_probs.numpy()[:want["probs"].shape[0]], want["probs"], rtol=RTOL)
