@@ -70,7 +70,7 @@ def test_lap_with_duals(gpu_api):
 def _compare_batch(api, oracle, pb, k, **kw):
     res = api.murty_batch(pb, k, **kw)
     cut = kw.get("cut_mode", api.CUT_RELATIVE) == api.CUT_RELATIVE
-    want = oracle.batch(pb, k, threads=8, want_probs=False, want_lists=True) if cut else None
+    want = oracle.batch(pb, k, cutoff=kw.get("cutoff", 42.0), threads=8, want_probs=False, want_lists=True) if cut else None
     bad = []
     for p in range(len(pb)):
         r4c, c4r, gain = res.lists(pb, p)
@@ -278,3 +278,38 @@ def test_c_abi_error_paths(gpu_api):
     assert rc == -4 and b"workspace" in lib.pda_last_error()
     with pytest.raises(_lib.PdaError):
         gpu_api.kBest2D(5, np.zeros((2, 3)))          # more columns than rows
+
+
+def test_fuzz_shapes_cutmodes_vs_oracle(gpu_api, oracle):
+    """Seeded fuzz over everything the two kernels branch on: 1x1 ... 24x9 problems, sparse +inf patterns (including
+    infeasible ones), exact-tie grids, tiny and huge k, relative cut-offs from 0 to 60, minimise and maximise."""
+    rng = np.random.default_rng(20260217)
+    for trial in range(12):
+        mats = []
+        for _ in range(160):
+            nM = int(rng.integers(1, 10))
+            nL = int(rng.integers(0, 16))
+            C = np.full((nL + nM, nM), np.inf)
+            kind = int(rng.integers(0, 4))
+            if kind == 0:
+                land = rng.uniform(0, 40, size=(nL, nM))
+            elif kind == 1:
+                land = np.floor(rng.uniform(0, 6, size=(nL, nM)))                      # many exact ties
+            elif kind == 2:
+                land = np.where(rng.random((nL, nM)) < 0.5, np.inf, rng.uniform(0, 30, size=(nL, nM)))  # gated entries
+            else:
+                land = rng.uniform(0, 1, size=(nL, nM)) * 10.0 ** rng.integers(-3, 4)
+            C[:nL, :] = land
+            dummy = rng.random(nM) < 0.85                                              # some detections cannot be missed
+            C[nL + np.arange(nM), np.arange(nM)] = np.where(dummy, float(rng.choice([10.0, 3.0, 0.5])), np.inf)
+            mats.append(C)
+        pb = synth.pack(mats, [m.shape[0] - m.shape[1] for m in mats])
+        k = int(rng.choice([1, 2, 7, 33, 150]))
+        mode = trial % 3
+        if mode == 0:
+            _compare_batch(gpu_api, oracle, pb, k, cutoff=float(rng.choice([0.0, 1.5, 42.0, 60.0])))
+        elif mode == 1:
+            _compare_batch(gpu_api, oracle, pb, k, cut_mode=gpu_api.CUT_NONE)
+        else:
+            neg = synth.pack([np.where(np.isfinite(m), -m, -np.inf) for m in mats], [m.shape[0] - m.shape[1] for m in mats])
+            _compare_batch(gpu_api, oracle, neg, k, cut_mode=gpu_api.CUT_NONE, maximize=True)
