@@ -26,6 +26,7 @@
 namespace pda {
 #ifdef PDA_CTA_PROFILE
 __device__ long long g_prof[16];
+__device__ long long g_trace[64 * 4];  // per round: warp-0 cycles, warp-1 task cycles, tasks, sweep after the round
 #endif
 namespace {
 
@@ -401,7 +402,8 @@ __device__ void serial_phase(const MurtyArgs& a, const CtaGeometry& cg, const Ct
     if (ctl->done[round & 1]) return;
 
     // Picking costs this warp ~3 000 cycles and it is the critical path, so it is skipped while enough splits are
-    // already waiting (done or in flight) and the top of the heap is among them.
+    // already waiting (done or in flight) and the top of the heap is among them.  (Picking again while the top's
+    // children are being solved finds almost nothing new among the first 32 entries: measured, no gain.)
     if (pad_record(heap.get(0).pad) != 0 && 64 - __popcll(ctl->freeRec) >= CTA_AHEAD) {
         if (lane == 0) { ctl->flight[(round + 1) & 1] = 0ULL; ctl->nTasks[(round + 1) & 1] = 0; }
         return;
@@ -553,14 +555,20 @@ __device__ void solve_problem_cta(const MurtyArgs& a, const CtaGeometry& cg, con
     // picked one round earlier; one barrier per round.  Round 0 only picks (the root's split).
     for (int round = 0; !doneAtRoot; ++round) {
         if (warp == 0) {
+#ifdef PDA_CTA_PROFILE
+            const long long tw0 = PROF_T();
+#endif
             serial_phase(a, cg, S, heap, A, nc, round, lane);
+#ifdef PDA_CTA_PROFILE
+            if (lane == 0 && round < 64) { g_trace[4 * round] = PROF_T() - tw0; g_trace[4 * round + 3] = ctl->sweep; }
+#endif
         } else {
             const int nT = ctl->nTasks[round & 1];
             const long long tt0 = PROF_T();
             for (int t = warp - 1; t < nT; t += CTA_WARPS - 1)
                 run_task<R>(a, S, sm, A, S.tasks[(round & 1) * CTA_MAXTASKS + t], n, nc, lane);
 #ifdef PDA_CTA_PROFILE
-            if (threadIdx.x == 32) ctl->tTasks += PROF_T() - tt0;
+            if (threadIdx.x == 32) { ctl->tTasks += PROF_T() - tt0; if (round < 64) { g_trace[4 * round + 1] = PROF_T() - tt0; g_trace[4 * round + 2] = nT; } }
 #endif
         }
         __syncthreads();
@@ -696,5 +704,8 @@ int launch_murty_cta(const MurtyArgs& a, const CtaGeometry& cg, cudaStream_t str
 #ifdef PDA_CTA_PROFILE
 extern "C" int pda_debug_read_prof(long long* out) {
     return (int)cudaMemcpyFromSymbol(out, pda::g_prof, sizeof(long long) * 16);
+}
+extern "C" int pda_debug_read_trace(long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, pda::g_trace, sizeof(long long) * 256);
 }
 #endif
