@@ -21,8 +21,9 @@
 
 std::vector<std::vector<double> > assignmentProb(const std::vector<double>& costMatrix, size_t nL, size_t nM, size_t k);
 
-/* permOpt: 1 exact, 2 "long" (same double kernel, as in the reference); 0 (Huber approximation) and anything
- * else throw std::runtime_error. */
+/* permOpt: 0 Huber's approximation (300 trials per sub-permanent, seeded counter-based draws instead of the reference's
+ * unseeded rand(): statistically equivalent, not sample for sample), 1 exact, 2 "long" (same double kernel, as in the
+ * reference); anything else throws std::runtime_error. */
 std::vector<std::vector<double> > permanentProb(std::vector<double> costMatrix, size_t nL, size_t nM, int permOpt);
 
 std::vector<std::vector<double> > bruteForceProb(const std::vector<double>& costMatrix, size_t nL, size_t nM);

@@ -6,9 +6,11 @@
  * column-major forms below them are always available and are what the Eigen forms call.
  * Matrices above dimension 32 throw std::runtime_error with the reference's message (nwPerm.cpp:329).
  *
- * Not provided: Huber's randomised approximation (permanentApproximation*, sinkhorn, hl_factor,
- * permanentFastest; nwPerm.cpp:19-211) -- it is driven by an unseeded rand() and is outside the
- * accelerated path; keep the reference's nwPerm.cpp for those symbols.
+ * Huber's randomised approximation (permanentApproximation / permanentApproximationSquare, nwPerm.cpp:126-211, with
+ * their sinkhorn / hl_factor / pickRowFromProbs helpers) is provided as well.  The reference draws from an unseeded
+ * process-wide rand(); here the draws are counter-based and seeded (pda_b200.h: pda_permanent_approx_batch), so the
+ * estimate is reproducible but agrees with the reference statistically, not sample for sample.  permanentFastest
+ * (nwPerm.cpp:19-33, never called by the reference) is the obvious switch over the two and is provided inline.
  */
 #ifndef sensSLAM_perm
 #define sensSLAM_perm
@@ -28,11 +30,17 @@
 /* raw forms: A is rows x cols, column-major */
 double permanentExactRaw(const double* A, size_t rows, size_t cols);
 long double permanentExactLongRaw(const double* A, size_t rows, size_t cols);
+double permanentApproximationRaw(const double* A, size_t rows, size_t cols, size_t iterations);
 
 #ifdef PDA_HAVE_EIGEN
 inline double permanentExact(const Eigen::MatrixXd& A) { return permanentExactRaw(A.data(), size_t(A.rows()), size_t(A.cols())); }
 inline double permanentExactSquare(const Eigen::MatrixXd& A) { return permanentExactRaw(A.data(), size_t(A.rows()), size_t(A.cols())); }
 inline long double permanentExactLong(const Eigen::MatrixXd& A) { return permanentExactLongRaw(A.data(), size_t(A.rows()), size_t(A.cols())); }
+inline double permanentApproximation(const Eigen::MatrixXd& A, size_t iterations) { return permanentApproximationRaw(A.data(), size_t(A.rows()), size_t(A.cols()), iterations); }
+inline double permanentApproximationSquare(const Eigen::MatrixXd& A, size_t iterations) { return permanentApproximationRaw(A.data(), size_t(A.rows()), size_t(A.cols()), iterations); }
+inline double permanentFastest(const Eigen::MatrixXd& A) {  /* nwPerm.cpp:19-33 */
+    return (A.rows() > A.cols() ? A.rows() : A.cols()) <= 20 ? permanentExact(A) : permanentApproximation(A, 300);
+}
 #endif
 
 #endif

@@ -221,8 +221,24 @@ int pda_permanent_range(const double* A, int32_t n, uint64_t begin, uint64_t end
 int pda_permanent_range_host(const double* A, int32_t n, uint64_t begin, uint64_t end, double* partial,
                              int32_t device);
 
+/* Huber's randomised approximation of the permanent: permanentApproximation / permanentApproximationSquare with their
+ * sinkhorn / hl_factor / pickRowFromProbs helpers (nwPerm.h:27-35, nwPerm.cpp:36-211), `iterations` acceptance /
+ * rejection trials per matrix (the reference uses apprxIter = 300, assignment.cpp:10).  Rectangular input is padded with
+ * ones and divided by (|rows-cols|)!; status[i] = 1 above dimension 32.  The reference draws from an unseeded global
+ * rand(); here every draw is a counter-based value keyed by (seed, matrix index, trial, column), so results are
+ * reproducible and independent of batch order -- agreement with the reference is statistical (same estimator, same
+ * trial count), not sample for sample.  pda_set_approx_seed sets the seed used where the reference signature has no
+ * room for one (permOpt == 0 below). */
+int pda_permanent_approx_batch(const double* mats, const int64_t* matOff, const int32_t* rows, const int32_t* cols,
+                               int64_t nMats, int32_t iterations, uint64_t seed, double* out, int32_t* status, void* stream);
+int pda_permanent_approx_batch_host(const double* mats, const int64_t* matOff, const int32_t* rows, const int32_t* cols,
+                                    int64_t nMats, int32_t iterations, uint64_t seed, double* out, int32_t* status,
+                                    int32_t device);
+void pda_set_approx_seed(uint64_t seed);
+
 /* conditionedPermanent (assignment.cpp:325-435) for a batch of matrices: zero rows/columns dropped,
- * columns scaled, permanent of the transpose, negative-result retry.  permOpt 1 or 2. */
+ * columns scaled, permanent of the transpose, negative-result retry.  permOpt 0 (Huber approximation, 300 trials),
+ * 1 (exact) or 2 ("long": the same double kernel, as in the reference); anything else sets status (the reference throws). */
 int pda_conditioned_permanent_batch_host(const double* mats, const int64_t* matOff, const int32_t* rows,
                                          const int32_t* cols, int64_t nMats, int32_t permOpt,
                                          double* out, int32_t* status, int32_t device);

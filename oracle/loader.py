@@ -47,6 +47,7 @@ class CpuChecker:
         f("bb_cost_matrix", None, [_ptr, C.c_long, _ptr, C.c_long, _dbl, _ptr])
         f("asgn_bb", None, [_ptr, C.c_long, _ptr, C.c_long, _dbl, _ptr])
         if prefix == "orc":  # restatement only: needs Eigen on the reference side (oracle_quadric.c)
+            f("permanent_approx", _dbl, [_ptr, _i64, _i64, _i64, C.c_uint64, _i64, _ptr])
             f("quadric_covs", None, [_ptr, _i64, _ptr])
             f("quadric_cost_matrix", None, [_ptr, _ptr, _i64, _ptr, _ptr, _i64, _dbl, _ptr])
             f("association_from_moments", _int, [_ptr, _ptr, _i64, _ptr, _ptr, _i64, _dbl, _i64, _ptr])
@@ -179,6 +180,13 @@ class CpuChecker:
         out = np.full(max(bl.shape[0], 1), -7, np.int32)
         self._asgn_bb(_p(bl), bl.shape[0], _p(br), br.shape[0], float(nonassign), _p(out))
         return out[:bl.shape[0]]
+
+    # ---- Huber's approximate permanent (restatement only; counter-based draws shared with the CUDA kernel) ----
+    def permanent_approx(self, a, iterations=300, seed=20260217, mat_index=0):
+        a = np.asfortranarray(a, dtype=np.float64)
+        succ = C.c_int64(0)
+        est = self._permanent_approx(_p(a), a.shape[0], a.shape[1], int(iterations), int(seed), int(mat_index), C.byref(succ))
+        return float(est), int(succ.value)
 
     # ---- cost matrices from quadric moments (restatement only) ---------------------------
     def quadric_covs(self, quadrics):

@@ -168,6 +168,7 @@ int orc_permanent_prob(const double* costsIn, int64_t nL, int64_t nM, int permOp
         double colPerm = 0;
         for (int64_t l = 0; l < nL && !status; l++) {
             if (P[l + m * nR] != 0) {
+                orc_set_approx_stream(20260217ULL, m * W + l);
                 double t = P[l + m * nR] * orc_conditioned_permanent(S, sR, sC, permOpt, &status);
                 colPerm += fabs(t);
                 probs[m * W + l] = fabs(t);
@@ -176,6 +177,7 @@ int orc_permanent_prob(const double* costsIn, int64_t nL, int64_t nM, int permOp
         }
         if (status) break;
         if (m != 0) S[(nL - 1 + m) + 0 * sR] = P[nL + 0 * nR]; /* :237-239 */
+        orc_set_approx_stream(20260217ULL, m * W + nL);
         double t = P[(nL + m) + m * nR] * orc_conditioned_permanent(S, sR, sC, permOpt, &status);
         colPerm += fabs(t);
         probs[m * W + nL] = fabs(t);

@@ -57,6 +57,13 @@ int orc_permanent_prob(const double* costs, int64_t nL, int64_t nM, int permOpt,
 /* assignment.cpp:57-74 (getAssignmentProbs after the cost matrix has been built). Returns 0, or 1 where the reference throws. */
 int orc_association_probs(const double* costs, int64_t nL, int64_t nM, int64_t k, int usePerm, double* probs);
 
+/* oracle_perm_approx.c: Huber's approximate permanent (nwPerm.cpp:36-211) with the CUDA kernel's counter-based draws
+ * in place of the reference's unseeded rand().  No `ref_` twin. */
+double orc_permanent_approx(const double* A, int64_t rows, int64_t cols, int64_t iterations, uint64_t seed, int64_t matIndex,
+                            int64_t* successesOut);
+/* which stream the next conditionedPermanent(.., permOpt = 0) draws from (thread-local index) */
+void orc_set_approx_stream(uint64_t seed, int64_t index);
+
 /* oracle_quadric.c: getCovs (assignment.cpp:693-703), computeQuadricCostMatrix (:705-722, the 3x3 Eigen LDLT solve
  * restated -- parity unpinned, see that file), getAssignmentProbs from the moments on (:38-74).  No `ref_` twins. */
 void orc_quadric_covs(const double* Q, int64_t n, double* covs);

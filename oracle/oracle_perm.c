@@ -93,9 +93,16 @@ double orc_permanent_exact_long(const double* A, int64_t rows, int64_t cols, int
  * its end and addresses Ascaled by the uncompacted column index (:384-392, undefined
  * behaviour).  Here zero columns are compacted away, which is
  * what the code evidently intends; parity tests avoid such inputs. */
+/* permOpt == 0 (Huber's approximation, apprxIter = 300, assignment.cpp:10/:401) draws from the counter-based stream of
+ * oracle_perm_approx.c; the stream's matrix index is set by the caller (the item index m*(nL+1)+l of permanentProb, 0 for
+ * a plain conditionedPermanent call), mirroring how the CUDA pipeline numbers its items. */
+static __thread int64_t g_approxIndex = 0;
+static uint64_t g_approxSeed = 20260217ULL;
+void orc_set_approx_stream(uint64_t seed, int64_t index) { g_approxSeed = seed; g_approxIndex = index; }
+
 double orc_conditioned_permanent(const double* A, int64_t rows, int64_t cols, int permOpt, int* status) {
     *status = 0;
-    if (permOpt != 1 && permOpt != 2) { *status = 1; return 0.0; }  /* 0 = Huber (out of scope); others throw (:406) */
+    if (permOpt < 0 || permOpt > 2) { *status = 1; return 0.0; }  /* the reference throws (:406) */
     int64_t* keepC = (int64_t*)malloc((size_t)(cols > 0 ? cols : 1) * sizeof(int64_t));
     int64_t* keepR = (int64_t*)malloc((size_t)(rows > 0 ? rows : 1) * sizeof(int64_t));
     double* colScale = (double*)malloc((size_t)(cols > 0 ? cols : 1) * sizeof(double));
@@ -127,7 +134,11 @@ double orc_conditioned_permanent(const double* A, int64_t rows, int64_t cols, in
         }
     }
     double result;
-    if (permOpt == 1) {
+    if (permOpt == 0) {
+        const int64_t dim = nKC > nKR ? nKC : nKR;
+        if (dim > 32) *status = 1;  /* device limit of the approximation kernel (the reference has none) */
+        result = *status ? 0.0 : orc_permanent_approx(St, nKC, nKR, 300, g_approxSeed, g_approxIndex, NULL) / scaleFactor;
+    } else if (permOpt == 1) {
         result = orc_permanent_exact(St, nKC, nKR, status) / scaleFactor;
         if (!*status && result < 0) result = orc_permanent_exact(S, nKR, nKC, status) / scaleFactor;
     } else {

@@ -47,6 +47,9 @@ SIGNATURES = {
     "pda_permanent_batch_host": (C.c_int, [ptr, ptr, ptr, ptr, i64, ptr, ptr, i32]),
     "pda_permanent_range": (C.c_int, [ptr, i32, u64, u64, ptr, ptr, i64, ptr]),
     "pda_permanent_range_host": (C.c_int, [ptr, i32, u64, u64, ptr, i32]),
+    "pda_permanent_approx_batch": (C.c_int, [ptr, ptr, ptr, ptr, i64, i32, u64, ptr, ptr, ptr]),
+    "pda_permanent_approx_batch_host": (C.c_int, [ptr, ptr, ptr, ptr, i64, i32, u64, ptr, ptr, i32]),
+    "pda_set_approx_seed": (None, [u64]),
     "pda_conditioned_permanent_batch_host": (C.c_int, [ptr, ptr, ptr, ptr, i64, i32, ptr, ptr, i32]),
     "pda_permanent_prob_batch_host": (C.c_int, [ptr, ptr, ptr, ptr, i64, i32, ptr, ptr, ptr, i32]),
 }

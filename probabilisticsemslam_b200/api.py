@@ -155,6 +155,24 @@ def permanent_batch(mats: list[np.ndarray], device: int = 0):
     return out, st
 
 
+def permanent_approx_batch(mats: list[np.ndarray], iterations: int = 300, seed: int = 20260217, device: int = 0):
+    """Huber's approximate permanent (nwPerm.cpp:126-211) for a list of (rows, cols) matrices -> (estimates, status)."""
+    flat = [np.asfortranarray(m, dtype=np.float64).reshape(-1, order="F") for m in mats]
+    sizes = np.asarray([f.size for f in flat], np.int64)
+    off = _prefix(sizes)
+    buf = np.ascontiguousarray(np.concatenate(flat)) if flat else np.zeros(1)
+    rows = np.asarray([m.shape[0] for m in mats], np.int32)
+    cols = np.asarray([m.shape[1] for m in mats], np.int32)
+    out, st = np.zeros(len(mats)), np.zeros(len(mats), np.int32)
+    check(lib().pda_permanent_approx_batch_host(_p(buf), _p(off), _p(rows), _p(cols), len(mats), int(iterations), int(seed),
+                                                _p(out), _p(st), device))
+    return out, st
+
+
+def permanentApproximation(A: np.ndarray, iterations: int = 300, seed: int = 20260217, device: int = 0) -> float:
+    return float(permanent_approx_batch([A], iterations, seed, device)[0][0])
+
+
 def conditioned_permanent_batch(mats: list[np.ndarray], perm_opt: int = 1, device: int = 0):
     n = len(mats)
     rows = np.asarray([m.shape[0] for m in mats], np.int32)

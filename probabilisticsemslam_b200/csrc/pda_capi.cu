@@ -48,6 +48,9 @@ int current_device_info(DeviceInfo* out) {
     return PDA_OK;
 }
 
+static std::atomic<uint64_t> g_approxSeed{20260217ULL};
+uint64_t approx_seed() { return g_approxSeed.load(); }
+
 std::mutex g_hostMu;
 std::vector<DevArena> g_arenas;
 std::vector<HostStreams> g_hostStreams;
@@ -98,6 +101,7 @@ double pda_diag_dfma_tflops(void) {
 }
 
 int pda_version(void) { return 100; }
+void pda_set_approx_seed(uint64_t seed) { g_approxSeed.store(seed); }
 const char* pda_last_error(void) { return g_err; }
 int pda_device_count(void) {
     int n = 0;

@@ -102,5 +102,11 @@ int launch_permanent_batch(const double* mats, const int64_t* matOff, const int3
 int launch_permanent_range(const double* A, int32_t n, uint64_t begin, uint64_t end, double* partial,
                            void* workspace, int64_t workspaceBytes, cudaStream_t stream);
 
+// ---- Huber's approximate permanent (permanent_approx_kernel.cu) -------------------------------------------------
+int launch_permanent_approx_batch(const double* mats, const int64_t* matOff, const int32_t* rows, const int32_t* cols,
+                                  int64_t nMats, int32_t iterations, uint64_t seed, double* out, int32_t* status,
+                                  cudaStream_t stream);
+uint64_t approx_seed();  // seed of the draws behind permOpt == 0 (pda_set_approx_seed)
+
 }  // namespace pda
 #endif

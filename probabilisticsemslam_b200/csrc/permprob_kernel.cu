@@ -228,13 +228,17 @@ struct ItemBuffers {
     double* perm; int32_t* permStatus; int32_t* negList; int32_t* negCount; void* ws; int64_t wsBytes;
 };
 
-int run_items(BuildArgs b, const ItemBuffers& ib, int64_t nItems, int maxDim, cudaStream_t s) {
+int run_items(BuildArgs b, const ItemBuffers& ib, int64_t nItems, int maxDim, int permOpt, cudaStream_t s) {
     b.subset = nullptr; b.nWork = nItems; b.transpose = 1;
     b.mats = ib.mats; b.outRows = ib.rows; b.outCols = ib.cols; b.scale = ib.scale; b.itemStatus = ib.status;
     build_items_kernel<<<(unsigned)((nItems + BUILD_WARPS - 1) / BUILD_WARPS), 32 * BUILD_WARPS, 0, s>>>(b);
     PDA_CUDA_TRY(cudaGetLastError());
-    PDA_TRY(launch_permanent_batch(ib.mats, ib.matOff, ib.rows, ib.cols, nItems, maxDim, ib.perm, ib.permStatus, ib.ws,
-                                   ib.wsBytes, s));
+    if (permOpt == 0)  // Huber's approximation, apprxIter = 300 trials (assignment.cpp:10, :401); never negative, so no retry
+        PDA_TRY(launch_permanent_approx_batch(ib.mats, ib.matOff, ib.rows, ib.cols, nItems, 300, approx_seed(), ib.perm,
+                                              ib.permStatus, s));
+    else
+        PDA_TRY(launch_permanent_batch(ib.mats, ib.matOff, ib.rows, ib.cols, nItems, maxDim, ib.perm, ib.permStatus, ib.ws,
+                                       ib.wsBytes, s));
     PDA_CUDA_TRY(cudaMemsetAsync(ib.negCount, 0, 4, s));
     unscale_kernel<<<(unsigned)((nItems + 255) / 256), 256, 0, s>>>(ib.perm, ib.scale, nullptr, nItems, ib.negList, ib.negCount);
     PDA_CUDA_TRY(cudaGetLastError());
@@ -299,7 +303,7 @@ int pda_conditioned_permanent_batch_host(const double* mats, const int64_t* matO
     if (nMats < 0) return fail(PDA_ERR_INVALID, "conditioned_permanent: nMats < 0");
     if (nMats == 0) return PDA_OK;
     if (!mats || !matOff || !rows || !cols || !out || !status) return fail(PDA_ERR_INVALID, "conditioned_permanent: NULL argument");
-    if (permOpt != 1 && permOpt != 2) {  // 0 = Huber approximation (out of scope); anything else throws (assignment.cpp:406)
+    if (permOpt < 0 || permOpt > 2) {  // 0 = Huber approximation, 1 = exact, 2 = "long"; anything else throws (assignment.cpp:406)
         for (int64_t i = 0; i < nMats; ++i) { out[i] = 0.0; status[i] = 1; }
         return PDA_OK;
     }
@@ -330,7 +334,7 @@ int pda_conditioned_permanent_batch_host(const double* mats, const int64_t* matO
     PDA_TRY(h2d(ib.matOff, slotOff.data(), n, s));
     BuildArgs b = {};
     b.mode = 1; b.P = st.at<double>(oA); b.pOff = st.at<int64_t>(oOff); b.rows = st.at<int32_t>(oR); b.cols = st.at<int32_t>(oC);
-    PDA_TRY(run_items(b, ib, nMats, maxDim, s));
+    PDA_TRY(run_items(b, ib, nMats, maxDim, permOpt, s));
     PDA_TRY(d2h(out, ib.perm, n, s));
     PDA_TRY(d2h(status, ib.status, n, s));
     PDA_CUDA_TRY(cudaStreamSynchronize(s));
@@ -343,7 +347,7 @@ int pda_permanent_prob_batch_host(const double* costs, const int64_t* costOff, c
     if (nProblems < 0) return fail(PDA_ERR_INVALID, "permanent_prob: nProblems < 0");
     if (nProblems == 0) return PDA_OK;
     if (!costs || !costOff || !nL || !nM || !probs || !probOff || !status) return fail(PDA_ERR_INVALID, "permanent_prob: NULL argument");
-    const bool throws = (permOpt != 1 && permOpt != 2);
+    const bool throws = (permOpt < 0 || permOpt > 2);
     // chunk the batch so that one chunk's items fit a bounded staging area
     const int64_t maxItemsPerChunk = 1 << 16;
     std::lock_guard<std::mutex> lk(g_hostMu);
@@ -411,7 +415,7 @@ int pda_permanent_prob_batch_host(const double* costs, const int64_t* costOff, c
                 BuildArgs b = {};
                 b.mode = 0; b.P = st.at<double>(oP); b.pOff = st.at<int64_t>(oOff); b.nL = st.at<int32_t>(oL); b.nM = st.at<int32_t>(oM);
                 b.itemOff = st.at<int64_t>(oItemOff); b.itemProblem = st.at<int32_t>(oItemProb);
-                PDA_TRY(run_items(b, ib, items, maxDim, s));
+                PDA_TRY(run_items(b, ib, items, maxDim, permOpt, s));
             }
             finish_probs_kernel<<<(unsigned)((n + BUILD_WARPS - 1) / BUILD_WARPS), 32 * BUILD_WARPS, 0, s>>>(
                 st.at<double>(oP), st.at<int64_t>(oOff), st.at<int32_t>(oL), st.at<int32_t>(oM), st.at<int64_t>(oItemOff), ib.perm,

@@ -67,7 +67,7 @@ std::vector<std::vector<double> > permanentProb(std::vector<double> costMatrix, 
                                            pdaShimDevice()),
              "permanentProb");
     if (status) {
-        if (permOpt == 1 || permOpt == 2)
+        if (permOpt >= 0 && permOpt <= 2)
             throw std::runtime_error("Maximum matrix dimension limited to 32. Error inside permanentExactSquare().");
         throw std::runtime_error("Unknown perm option in conditioned permanent!");
     }
@@ -165,10 +165,23 @@ double conditionedPermanentRaw(const double* A, size_t rows, size_t cols, int pe
     pdaCheck(pda_conditioned_permanent_batch_host(A, &off, &r, &c, 1, permOpt, &out, &status, pdaShimDevice()),
              "conditionedPermanent");
     if (status) {
-        if (permOpt == 1 || permOpt == 2)
+        if (permOpt >= 0 && permOpt <= 2)
             throw std::runtime_error("Maximum matrix dimension limited to 32. Error inside permanentExactSquare().");
         throw std::runtime_error("Unknown perm option in conditioned permanent!");
     }
+    return out;
+}
+
+double permanentApproximationRaw(const double* A, size_t rows, size_t cols, size_t iterations) {
+    static uint64_t calls = 0;  // successive calls draw from successive streams, like successive rand() calls would
+    const int64_t off = 0;
+    const int32_t r = int32_t(rows), c = int32_t(cols);
+    int32_t status = 0;
+    double out = 0;
+    pdaCheck(pda_permanent_approx_batch_host(A, &off, &r, &c, 1, int32_t(iterations), 20260217ULL + (calls++), &out, &status,
+                                             pdaShimDevice()),
+             "permanentApproximation");
+    if (status) throw std::runtime_error("permanentApproximation: matrix dimension limited to 32 on the device");
     return out;
 }
 
