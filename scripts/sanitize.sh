@@ -23,6 +23,8 @@ A = synth.dense_square(3, 10)
 print("perm", api.permanent_batch([a.reshape(10, 10, order="F") for a in A])[0])
 print("range", api.permanent_range(A[0].reshape(10, 10, order="F"), 0, 512))
 print("lap", api.assign2D(pb.matrix(0))[0])
+print("approx", api.permanent_approx_batch([a.reshape(10, 10, order="F") for a in A], 40)[0])
+print("permprob approx", len(api.permanent_prob_batch(sub, 0)[0]))
 PY
 for tool in ${SAN_TOOLS:-memcheck racecheck synccheck}; do
   echo "=== $tool"
