@@ -67,3 +67,24 @@ def test_same_caller_two_backends(tmp_path, gpu_api):
             np.testing.assert_allclose(fb, fa, rtol=1e-6, atol=1e-300)   # ill-conditioned NW sums: see test_gpu_permanent
         else:
             np.testing.assert_allclose(fb, fa, rtol=1e-9, atol=0)
+
+
+def test_moments_and_approximation_through_the_cpp_headers(gpu_api, oracle):
+    """computeQuadricCostMatrixRaw, getAssignmentProbsFromMoments and permanentApproximationRaw (include/assignment.h,
+    include/nwPerm.h) from a C++ caller: same numbers as the Python face of the library and as the CPU oracle."""
+    exe = os.path.join(ROOT, "tests", "cpp", "build", "moments_b200")
+    assert os.path.exists(exe), "tests/cpp/build/moments_b200 missing: run __graft_entry__.build()"
+    lm, lc, mm, mc = synth.quadric_frames(1, first=31)[0]
+    col = lambda c: c.transpose(0, 2, 1).reshape(-1)          # column-major 3x3, Eigen's layout
+    text = f"{lm.shape[0]} {mm.shape[0]} 10.0 200\n" + " ".join(repr(float(x)) for x in
+                                                                np.concatenate([lm.reshape(-1), col(lc), mm.reshape(-1), col(mc)]))
+    run = subprocess.run([exe], input=text, capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stderr[-500:]
+    lines = {ln.split()[0] + (" " + ln.split()[1] if ln.startswith("probs") else ""): ln.split() for ln in run.stdout.splitlines()}
+    costs = np.array([float(x) for x in lines["costs"][1:]]).reshape((lm.shape[0] + mm.shape[0], mm.shape[0]), order="F")
+    want = oracle.quadric_cost_matrix(lm, lc, mm, mc, 10.0)
+    np.testing.assert_array_equal(costs.view(np.int64), want.view(np.int64))
+    probs = np.array([[float(x) for x in lines[f"probs {m}"][2:]] for m in range(mm.shape[0])])
+    np.testing.assert_array_equal(probs, gpu_api.getAssignmentProbs(lm, lc, mm, mc, 10.0, 200))
+    np.testing.assert_allclose(probs, oracle.association_from_moments(lm, lc, mm, mc, 10.0, 200), rtol=1e-9, atol=1e-300)
+    assert abs(float(lines["approx"][1]) / 720.0 - 1.0) < 0.2     # 300 trials, ~68 % accepted: 4 % standard error
