@@ -284,7 +284,9 @@ __device__ void root_phase(const MurtyArgs& a, const long long p, const CtaSmem&
 #pragma unroll
     for (int s = 0; s < R; ++s) if (lane + 32 * s < n) allRows |= 1u << s;
     for (int c = 0; c < n; ++c) {
-        if (augment_from<R>(c, nc, n, sm, nd, allRows, 0u, lane)) {
+        const bool stuck = augment_from<R>(c, nc, n, sm, nd, allRows, 0u, lane);
+        publish_cols<R>(sm, nd, lane);  // the next column starts from this solution
+        if (stuck) {
             if (lane == 0) { a.nFound[p] = 0; ctl->feasible = 0; ctl->done[0] = ctl->done[1] = 1; ctl->nFound = 0; ctl->nEmit = 0; }
             if (wantW && nc > 1) {
                 double* out = a.probs + a.probOff[p];
@@ -503,7 +505,7 @@ __device__ void run_task(const MurtyArgs& a, const CtaSmem& S, const WarpSmem& s
     if (c == a0) hideFirst = parForb;
     __syncwarp();
     double result = CUDART_NAN;  // NaN = no child (infeasible or cut)
-    const bool infeasible = augment_from<R, true>(c, nc, n, sm, nd, inPar, hideFirst, lane);
+    const bool infeasible = augment_from<R>(c, nc, n, sm, nd, inPar, hideFirst, lane);
     if (!infeasible) {
         const double g = path_gain_reg<R>(sm, nd, n, nc, lane);
         const double cutoffGain = S.ctl->cutoffGain;

@@ -179,11 +179,12 @@ __device__ __forceinline__ int fast_forward(const int numColReal, const WarpSmem
 // arg-min skips it, and "scanned" can be read back from it afterwards.  The cost at which a row was
 // scanned (== delta at that moment) is parked in sm.spc by lane 0, where the dual update reads it.
 //
-// CHILD = a Murty child solve: the mirrors in shared memory hold the PARENT's u / row4col / col4row and are left
-// that way (the next child of the same split starts from the same parent), so the dual update and the flip touch the
-// registers only; uRowPar, when given, is the parent's "u of the column each row is paired with", computed once per
-// split (the freed row's entry is stale there, but a free row is a stopper and never consulted).
-template <int R, bool CHILD = false>
+// The mirrors in shared memory (u / row4col / col4row of the node the search STARTS from) are read, never written:
+// the dual update and the flip touch the registers only.  A Murty split publishes the parent once and solves all its
+// children against it; the root LAP republishes after every column.  uRowPar, when given, is the start node's "u of the
+// column each row is paired with", computed once per split (the freed row's entry is stale there, but a free row is a
+// stopper and never consulted).
+template <int R>
 __device__ __forceinline__ bool augment_from(const int startCol, const int numColReal, const int ld,
                                              const WarpSmem& sm, Node<R>& nd, const unsigned scanBits,
                                              const unsigned forbBits, const int lane, const double* uRowPar = nullptr) {
@@ -263,8 +264,8 @@ __device__ __forceinline__ bool augment_from(const int startCol, const int numCo
             for (int q = 1; q < R; ++q) if ((r >> 5) == q) w = rowsDone[q];
             seen = (w >> (r & 31)) & 1u;
         }
-        if (c == startCol) { nd.u[s] = nd.u[s] + delta; if (!CHILD) sm.u[c] = nd.u[s]; }
-        else if (seen) { nd.u[s] = (nd.u[s] + delta) - sm.spc[r]; if (!CHILD) sm.u[c] = nd.u[s]; }
+        if (c == startCol) nd.u[s] = nd.u[s] + delta;
+        else if (seen) nd.u[s] = (nd.u[s] + delta) - sm.spc[r];
     }
     // flip along the predecessor chain (:108-116); sm.r4c still holds the pre-flip pairing
     int r = sink, c;
@@ -278,15 +279,7 @@ __device__ __forceinline__ bool augment_from(const int startCol, const int numCo
         }
         r = h;
     } while (c != startCol);
-    __syncwarp();
-    if (!CHILD) {
-#pragma unroll
-        for (int s = 0; s < R; ++s) {
-            sm.r4c[lane + 32 * s] = (short)nd.r4c[s];
-            sm.c4r[lane + 32 * s] = (unsigned short)nd.c4r[s];
-        }
-        __syncwarp();
-    }
+    __syncwarp();  // the chain walk has read sm.pred / sm.r4c before anybody rewrites them
     return false;
 }
 

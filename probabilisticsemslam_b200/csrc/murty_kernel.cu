@@ -70,7 +70,9 @@ __device__ void solve_problem(const MurtyArgs& a, const long long p, const WarpS
 #pragma unroll
     for (int s = 0; s < R; ++s) if (lane + 32 * s < n) allRows |= 1u << s;
     for (int c = 0; c < n; ++c) {
-        if (augment_from<R>(c, nc, n, sm, nd, allRows, 0u, lane)) {
+        const bool stuck = augment_from<R>(c, nc, n, sm, nd, allRows, 0u, lane);
+        publish_cols<R>(sm, nd, lane);  // the next column starts from this solution
+        if (stuck) {
             if (lane == 0) a.nFound[p] = 0;
             if (wantW && nc > 1) {  // the reference ends up scaling zeros by 1/0 here
                 double* out = a.probs + a.probOff[p];
@@ -136,7 +138,7 @@ __device__ void solve_problem(const MurtyArgs& a, const long long p, const WarpS
             }
             hideFirst = (c == a0) ? parForb : mine;  // first child inherits every constraint on the active column (:490)
             __syncwarp();
-            const bool infeasible = augment_from<R, true>(c, nc, n, sm, nd, inPar, hideFirst, lane, uRowPar);
+            const bool infeasible = augment_from<R>(c, nc, n, sm, nd, inPar, hideFirst, lane, uRowPar);
 #pragma unroll
             for (int s = 0; s < R; ++s) if ((mine >> s) & 1u) sm.c4r[lane + 32 * s] = (unsigned short)c;  // the parent's pairing again
             if (!infeasible) {
@@ -274,7 +276,10 @@ __global__ void lap_kernel(const LapArgs a, const int smemPerWarp, const int cCa
 #pragma unroll
     for (int s = 0; s < R; ++s) if (lane + 32 * s < n) allRows |= 1u << s;
     bool infeasible = false;
-    for (int c = 0; c < nc && !infeasible; ++c) infeasible = augment_from<R>(c, nc, n, sm, nd, allRows, 0u, lane);
+    for (int c = 0; c < nc && !infeasible; ++c) {
+        infeasible = augment_from<R>(c, nc, n, sm, nd, allRows, 0u, lane);
+        publish_cols<R>(sm, nd, lane);
+    }
     double gain = -1.0;
     int r0 = -1;
     if (!infeasible) {
