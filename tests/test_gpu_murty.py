@@ -313,3 +313,23 @@ def test_fuzz_shapes_cutmodes_vs_oracle(gpu_api, oracle):
         else:
             neg = synth.pack([np.where(np.isfinite(m), -m, -np.inf) for m in mats], [m.shape[0] - m.shape[1] for m in mats])
             _compare_batch(gpu_api, oracle, neg, k, cut_mode=gpu_api.CUT_NONE, maximize=True)
+
+
+def test_full_size_every_hypothesis_vs_reference(gpu_api, oracle):
+    """BASELINE.json configs[1] in full: all 100 000 problems, all 200 hypotheses each (2e7 index lists and gains), bit
+    for bit against the reference's own code compiled IEEE-strict when oracle/_ref travelled to this box, else against
+    the C restatement; weights to 1e-9.  ~15 s per kernel (the CPU side runs on all host threads)."""
+    import os
+    from oracle.loader import load_reference, reference_available
+    chk = load_reference("strict") if reference_available("strict") else oracle
+    n_total, k, chunk = 100_000, 200, 10_000
+    for first in range(0, n_total, chunk):
+        pb = synth.g1_dense(chunk, first=first)
+        got = gpu_api.murty_batch(pb, k, weight_mode=gpu_api.WEIGHTS_GATED)
+        want = chk.batch(pb, k, threads=os.cpu_count(), want_probs=True, want_lists=True)
+        np.testing.assert_array_equal(got.n_found, want["n_found"])
+        assert np.array_equal(got.row4col, want["row4col"]), f"row4col differs in problems {first}..{first + chunk}"
+        assert np.array_equal(got.col4row, want["col4row"]), f"col4row differs in problems {first}..{first + chunk}"
+        valid = (np.arange(k)[None, :] < want["n_found"][:, None]).reshape(-1)
+        assert not np.any((got.gain.reshape(-1).view(np.int64) != want["gain"].view(np.int64)) & valid), "gain bits differ"
+        np.testing.assert_allclose(got.probs, want["probs"], rtol=1e-9, atol=0)
