@@ -9,16 +9,18 @@
 // out-of-order execution with in-order commit:
 //
 //   * a node's split (shortestPathCPP.cpp:455-532) depends only on the node itself, so it can be done
-//     BEFORE the node reaches the top of the queue.  Every round, warp 0 picks the cheapest not-yet-split
-//     nodes near the top of the heap (the top itself first) and turns each (node, child column) pair
-//     into a task; the 16 warps solve the tasks in parallel (one Dijkstra each) and leave the children's
-//     gains in a split record;
-//   * warp 0 then replays the reference's loop strictly in order -- pop, push the popped node's
-//     children in column order, read the new top -- for as long as the top's split record exists.  The
-//     heap therefore sees exactly the reference's sequence of push/pop operations, including the
-//     order among exactly equal gains.
+//     BEFORE the node reaches the top of the queue.  Warp 0 picks the cheapest not-yet-split nodes among
+//     the first 32 heap entries (the top itself first) and turns each (node, child column) pair into a
+//     task; warps 1-15 solve the tasks (one Dijkstra each) in the NEXT round and leave the children's
+//     gains in a split record in shared memory;
+//   * warp 0 replays the reference's loop strictly in order -- pop, push the popped node's children in
+//     column order, read the new top -- for as long as the top's split record exists and is not being
+//     solved in the current round.  The heap therefore sees exactly the reference's sequence of push/pop
+//     operations, including the order among exactly equal gains.  Commit and child solves overlap: task
+//     lists, done flags and in-flight masks are double-buffered by round parity, one barrier per round.
 //   On the KITTI-shaped problems ~97 % of the speculated splits are consumed (a node close to the top
-//   is almost always popped within the next few sweeps), and 199 sweeps take ~30 rounds.
+//   is almost always popped within the next few sweeps): 199 sweeps are committed in ~23 bursts, each
+//   ended by a freshly created child becoming the top (its split cannot have been computed ahead).
 //   * lists and weights are written at the end, by all warps, from the recorded pop order; weights are
 //     accumulated per table entry in hypothesis order, i.e. in the reference's order (assignment.cpp:620-640).
 #include "murty_device.cuh"
@@ -81,7 +83,6 @@ struct CtaSmem {
     unsigned char* mirrors;  // CTA_WARPS x mirrorBytes
     double* recGain;         // [CTA_RECORDS][PDA_CTA_MAX_COL]
     int* recBase;            // [CTA_RECORDS]
-    int* recRound;           // [CTA_RECORDS] round in which the record's children are solved
     Task* tasks;             // [2][CTA_MAXTASKS]
     CtaCtl* ctl;
     HeapEntry* heapTop;
@@ -94,8 +95,7 @@ __device__ __forceinline__ CtaSmem carve_cta(unsigned char* base, const MurtyGeo
     s.mirrors = reinterpret_cast<unsigned char*>(s.acc + g.pCap);
     s.recGain = reinterpret_cast<double*>(s.mirrors + (size_t)CTA_WARPS * cg.mirrorBytes);
     s.recBase = reinterpret_cast<int*>(s.recGain + CTA_RECORDS * PDA_CTA_MAX_COL);
-    s.recRound = s.recBase + CTA_RECORDS;
-    s.tasks = reinterpret_cast<Task*>(s.recRound + CTA_RECORDS);
+    s.tasks = reinterpret_cast<Task*>(s.recBase + CTA_RECORDS);
     s.ctl = reinterpret_cast<CtaCtl*>(base + cg.ctlOff);
     s.heapTop = reinterpret_cast<HeapEntry*>(base + cg.heapTopOff);
     return s;
@@ -669,7 +669,7 @@ int murty_cta_geometry(int32_t k, int32_t maxNumRow, int32_t maxNumCol, bool wei
     cg->nodesOff = (cg->heapBytes + orderBytes + 255) / 256 * 256;
     cg->arenaStride = (cg->nodesOff + nodes * g->nodeStride + 255) / 256 * 256;
     int off = 8 * (g->cCap + g->pCap) + CTA_WARPS * cg->mirrorBytes + 8 * CTA_RECORDS * PDA_CTA_MAX_COL +
-              8 * CTA_RECORDS + 2 * (int)sizeof(Task) * CTA_MAXTASKS + 32;
+              4 * CTA_RECORDS + 2 * (int)sizeof(Task) * CTA_MAXTASKS + 32;
     off = round_up_i(off, 16);
     cg->ctlOff = off;
     off = round_up_i(off + (int)sizeof(CtaCtl), 16);
