@@ -283,7 +283,11 @@ def reference_available(kind: str = "strict") -> bool:
 def load_reference(kind: str = "strict") -> CpuChecker:
     """kind: 'strict' (IEEE, parity), 'fast' (-Ofast, x86-64-v3), 'native' (the reference's own
     -Ofast -march=native; refused when this host lacks ISA extensions of the build host),
-    'timing' (native if loadable here, else fast)."""
+    'timing' (native if loadable here, else fast).
+
+    The -Ofast builds ('fast', 'native', 'timing') are for TIMING on the dense benchmark inputs only: -ffast-math assumes
+    there is no infinity, and on gated matrices (most entries +inf after conditionCosts) the reference's own code then does
+    not terminate (observed: association_probs on synth.quadric_frames).  Use 'strict' for anything gated."""
     if kind == "timing":
         kind = "native" if (reference_available("native") and _native_ok()) else "fast"
     if kind == "native" and not _native_ok():
