@@ -13,19 +13,6 @@ namespace {
 
 constexpr int WARPS = 4;
 
-__global__ void sum_dims_kernel(const int32_t* __restrict__ nL, const int32_t* __restrict__ nM, int64_t n,
-                                int32_t* __restrict__ numRow) {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < n) numRow[p] = nL[p] + nM[p];
-}
-
-// condL = goodRows - nM (assignment.cpp:60)
-__global__ void cond_dims_kernel(const int32_t* __restrict__ goodRows, const int32_t* __restrict__ nM, int64_t n,
-                                 int32_t* __restrict__ condNL) {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < n) condNL[p] = goodRows[p] - nM[p];
-}
-
 // probs[m][rowIdx[l]] = cond[m][l] for l < condL; probs[m][nL] = cond[m][condL]; everything else 0 (:68-74).
 // nL == 0 -> {1} per detection (:51-53).  One warp per problem.
 __global__ void uncompact_probs_kernel(const double* __restrict__ cond, const int64_t* __restrict__ probOff,
@@ -91,12 +78,9 @@ int pda_association_probs_batch(const double* costs, const int64_t* costOff, con
     int64_t* rowIdx = reinterpret_cast<int64_t*>(w + o); o += align256((size_t)totalRows * 8);
     double* condProbs = reinterpret_cast<double*>(w + o); o += align256((size_t)totalProbElems * 8);
     if ((int64_t)o + 256 > workspaceBytes) return fail(PDA_ERR_WORKSPACE, "association: workspace too small");
-    const unsigned blocks = (unsigned)((n + 255) / 256);
-    sum_dims_kernel<<<blocks, 256, 0, s>>>(nL, nM, nProblems, numRow);
-    PDA_CUDA_TRY(cudaGetLastError());
-    PDA_TRY(launch_condition_costs(costs, costOff, numRow, nM, nProblems, rowOff, condCosts, rowIdx, goodRows, s));
-    cond_dims_kernel<<<blocks, 256, 0, s>>>(goodRows, nM, nProblems, condNL);
-    PDA_CUDA_TRY(cudaGetLastError());
+    // (numRow = nL + nM and condL = goodRows - nM are formed inside the conditioning kernel: two launches fewer)
+    (void)numRow;
+    PDA_TRY(launch_condition_costs(costs, costOff, nullptr, nM, nProblems, rowOff, condCosts, rowIdx, goodRows, s, nL, condNL));
     // conditioned problems live at the original cost offsets (they only shrink) and use the original probability offsets
     PDA_TRY(pda_murty_batch(condCosts, costOff, goodRows, nM, nProblems, maxNumRow, maxNumCol, k, PDA_CUT_RELATIVE, 42.0, 0, 0,
                             nullptr, nullptr, nullptr, nullptr, nullptr, nFound ? nFound : found, PDA_WEIGHTS_GATED, condProbs,

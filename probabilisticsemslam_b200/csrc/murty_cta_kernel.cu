@@ -637,6 +637,10 @@ __global__ void __launch_bounds__(32 * CTA_WARPS, 1) murty_cta_kernel(const Murt
     if ((int)blockIdx.x >= a.nWarps) return;  // nWarps = arenas available = CTAs allowed to run
     const CtaSmem S = carve_cta(smemRaw, a.geo, cg);
     unsigned char* arena = a.arena + (size_t)blockIdx.x * cg.arenaStride;
+    if (a.cursor == nullptr) {  // one CTA per problem and enough arenas for all of them: no work queue
+        solve_problem_cta<R>(a, cg, (long long)blockIdx.x, S, arena);
+        return;
+    }
     for (;;) {
         __syncthreads();  // the previous problem's readers of ctl are done
         if (threadIdx.x == 0) S.ctl->problem = (long long)atomicAdd(a.cursor, 1ULL);
@@ -691,8 +695,10 @@ static int launch_murty_cta_r(const MurtyArgs& a, const CtaGeometry& cg, cudaStr
     return PDA_OK;
 }
 
-int launch_murty_cta(const MurtyArgs& a, const CtaGeometry& cg, cudaStream_t stream) {
-    PDA_CUDA_TRY(cudaMemsetAsync(a.cursor, 0, sizeof(unsigned long long), stream));
+int launch_murty_cta(const MurtyArgs& args, const CtaGeometry& cg, cudaStream_t stream) {
+    MurtyArgs a = args;
+    if (a.nProblems <= a.nWarps) a.cursor = nullptr;  // every problem has its own CTA: skip the queue and its memset
+    else PDA_CUDA_TRY(cudaMemsetAsync(a.cursor, 0, sizeof(unsigned long long), stream));
     switch (a.geo.R) {
         case 1: return launch_murty_cta_r<1>(a, cg, stream);
         case 2: return launch_murty_cta_r<2>(a, cg, stream);

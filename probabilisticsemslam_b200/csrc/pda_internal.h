@@ -92,7 +92,8 @@ int launch_lap(const LapArgs& a, cudaStream_t stream);
 // ---- conditioning / likelihoods (weights_kernel.cu) --------------------------------------------
 int launch_condition_costs(const double* costs, const int64_t* costOff, const int32_t* numRow,
                            const int32_t* numCol, int64_t nProblems, const int64_t* rowOff,
-                           double* outCosts, int64_t* rowIdx, int32_t* goodRows, cudaStream_t stream);
+                           double* outCosts, int64_t* rowIdx, int32_t* goodRows, cudaStream_t stream,
+                           const int32_t* nLopt = nullptr, int32_t* condNL = nullptr);  // nLopt: numRow = nLopt + numCol
 int launch_to_probs(double* values, const int64_t* off, const int64_t* len, int64_t nVectors, cudaStream_t stream);
 
 // ---- permanents (permanent_kernel.cu) ------------------------------------------------------------

@@ -29,12 +29,14 @@ __global__ void condition_costs_kernel(const double* __restrict__ costs, const i
                                        const int32_t* __restrict__ numRow, const int32_t* __restrict__ numCol,
                                        const int64_t nProblems, const int64_t* __restrict__ rowOff,
                                        double* __restrict__ outCosts, int64_t* __restrict__ rowIdx,
-                                       int32_t* __restrict__ goodRows) {
+                                       int32_t* __restrict__ goodRows, const int32_t* __restrict__ nLopt,
+                                       int32_t* __restrict__ condNL) {
     __shared__ double colMinS[WARPS][PDA_MAX_DIM];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t p = (int64_t)blockIdx.x * WARPS + warp;
     if (p >= nProblems) return;
-    const int nR = numRow[p], nC = numCol[p];
+    const int nC = numCol[p];
+    const int nR = nLopt ? nLopt[p] + nC : numRow[p];  // the association pipeline passes nL and lets this kernel add
     const double* C = costs + costOff[p];
     double* colMin = colMinS[warp];
     for (int c = 0; c < nC; ++c) {
@@ -75,7 +77,10 @@ __global__ void condition_costs_kernel(const double* __restrict__ costs, const i
         }
         base += __popc(m);
     }
-    if (lane == 0) goodRows[p] = good;
+    if (lane == 0) {
+        goodRows[p] = good;
+        if (condNL) condNL[p] = good - nC;  // condL = goodRows - nM (assignment.cpp:60)
+    }
 }
 
 __global__ void to_probs_kernel(double* __restrict__ values, const int64_t* __restrict__ off,
@@ -98,10 +103,11 @@ __global__ void to_probs_kernel(double* __restrict__ values, const int64_t* __re
 
 int launch_condition_costs(const double* costs, const int64_t* costOff, const int32_t* numRow,
                            const int32_t* numCol, int64_t nProblems, const int64_t* rowOff,
-                           double* outCosts, int64_t* rowIdx, int32_t* goodRows, cudaStream_t stream) {
+                           double* outCosts, int64_t* rowIdx, int32_t* goodRows, cudaStream_t stream,
+                           const int32_t* nLopt, int32_t* condNL) {
     const int64_t ctas = (nProblems + WARPS - 1) / WARPS;
     condition_costs_kernel<<<(unsigned)ctas, 32 * WARPS, 0, stream>>>(costs, costOff, numRow, numCol, nProblems, rowOff,
-                                                                      outCosts, rowIdx, goodRows);
+                                                                      outCosts, rowIdx, goodRows, nLopt, condNL);
     PDA_CUDA_TRY(cudaGetLastError());
     return PDA_OK;
 }
