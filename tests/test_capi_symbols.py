@@ -33,7 +33,9 @@ def test_shim_library_exports_the_reference_entry_points():
     assert os.path.exists(path), "libpda_b200_shims.so missing: run __graft_entry__.build()"
     out = os.popen(f"nm -DC --defined-only {path}").read()
     for sym in ["kBest2D(", "kBest2DCutoff(", "assign2D(", "shortestPathCPP(", "assignmentProb(", "permanentProb(",
-                "bruteForceProb(", "conditionCosts(", "toProbs(", "conditionedPermanentRaw(", "permanentExactRaw("]:
+                "bruteForceProb(", "conditionCosts(", "toProbs(", "conditionedPermanentRaw(", "permanentExactRaw(",
+                "permanentApproximationRaw(", "computeQuadricCostMatrixRaw(", "getAssignmentProbsFromMoments(",
+                "getAssignmentProbsFromCosts(", "asgnBBRaw(", "assignmentProbBatch("]:
         assert sym in out, f"{sym} missing from the C++ drop-in layer"
 
 
@@ -47,6 +49,24 @@ def test_no_cpu_fallback():
         api.kBest2DCutoff(5, synth.g1_dense(1, nM=3).matrix(0))
     with pytest.raises(_lib.PdaError):
         api.permanentExact(np.ones((3, 3)))
+
+
+def test_host_side_knobs_work_without_a_device():
+    """Argument checking and the process-wide knobs are host logic: they must behave without a GPU."""
+    from probabilisticsemslam_b200 import _lib
+    lib = _lib.lib()
+    prev = lib.pda_murty_set_path(2)
+    assert prev in (0, 1, 2) and lib.pda_murty_set_path(prev) == 2
+    assert lib.pda_murty_set_path(7) == -1 and b"path" in lib.pda_last_error()
+    lib.pda_set_approx_seed(123)
+    lib.pda_set_approx_seed(20260217)
+    found = np.zeros(1, np.int32)
+    assert lib.pda_murty_batch_host(None, None, None, None, 1, 5, 0, 0.0, 0, 0, None, None, None, None, None,
+                                    found.ctypes.data, 0, None, None, None, 0) == -1          # NULL inputs
+    assert lib.pda_permanent_approx_batch_host(None, None, None, None, 1, 300, 1, None, None, 0) == -1
+    assert lib.pda_quadric_cost_batch_host(None, None, None, None, None, None, 1, 10.0, None, 0) == -1
+    assert lib.pda_murty_batch_host(None, None, None, None, 0, 5, 0, 0.0, 0, 0, None, None, None, None, None,
+                                    None, 0, None, None, None, 0) == 0                          # empty batch: nothing to do
 
 
 def test_product_never_imports_the_oracle():
