@@ -41,6 +41,32 @@ def test_oracle_estimator_against_exact(oracle):
     assert abs(est / 6.0 - 1.0) < 0.15
 
 
+def _golden_cases():
+    from helpers import golden
+    z = golden("perm_approx")
+    return [(z[f"A{i}"], float(z[f"est{i}"]), int(z[f"succ{i}"]), float(z[f"exact{i}"])) for i in range(int(z["n"]))], int(z["seed"])
+
+
+def test_oracle_reproduces_its_golden_stream(oracle):
+    """tests/golden/perm_approx.npz: estimates and success counts of the counter-based stream (regression pin of the
+    restatement and of the draw function both sides share)."""
+    cases, seed = _golden_cases()
+    for i, (A, est, succ, exact) in enumerate(cases):
+        got, s = oracle.permanent_approx(A, N_TRIALS, seed, i)
+        assert s == succ and abs(got / est - 1.0) < 1e-12
+        assert _within_binomial_error(est, exact, succ)
+
+
+@pytest.mark.gpu
+def test_gpu_against_golden_stream(gpu_api):
+    cases, seed = _golden_cases()
+    got, st = gpu_api.permanent_approx_batch([c[0] for c in cases], N_TRIALS, seed)
+    assert not st.any()
+    for g, (A, est, succ, exact) in zip(got, cases):
+        assert abs(g / est - 1.0) <= 3.0 / max(succ, 1) + 1e-9, (A.shape, g, est)
+        assert _within_binomial_error(g, exact, succ)
+
+
 @pytest.mark.gpu
 def test_gpu_against_restatement_and_exact(gpu_api, oracle):
     mats = _cases()

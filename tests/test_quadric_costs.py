@@ -59,6 +59,38 @@ def test_oracle_ldlt_against_numpy(oracle):
     assert worst < 1e-6
 
 
+def _golden_frames():
+    from helpers import golden
+    z = golden("quadric_costs")
+    for i in range(int(z["n"])):
+        yield (z[f"lm{i}"], z[f"lc{i}"], z[f"mm{i}"], z[f"mc{i}"]), z[f"cost{i}"], z[f"probs{i}"], float(z["nonassign"]), int(z["k"])
+
+
+def test_oracle_against_50_digit_truth(oracle):
+    """tests/golden/quadric_costs.npz holds the costs computed with 50 significant digits (mpmath) and rounded once:
+    a pin of the LDLT restatement that does not depend on any double-precision solver."""
+    for f, cost, probs, na, k in _golden_frames():
+        got = oracle.quadric_cost_matrix(*f, na)
+        fin = np.isfinite(cost)
+        assert np.array_equal(np.isfinite(got), fin)
+        np.testing.assert_allclose(got[fin], cost[fin], rtol=1e-12)
+        np.testing.assert_allclose(oracle.association_from_moments(*f, na, k), probs, rtol=1e-12, atol=1e-300)
+
+
+@pytest.mark.gpu
+def test_gpu_against_50_digit_truth(gpu_api):
+    frames, costs, probs = [], [], []
+    for f, cost, pr, na, k in _golden_frames():
+        frames.append(f); costs.append(cost); probs.append(pr)
+    got = gpu_api.quadric_cost_batch(frames, na)
+    for g, want in zip(got, costs):
+        fin = np.isfinite(want)
+        assert np.array_equal(np.isfinite(g), fin)
+        np.testing.assert_allclose(g[fin], want[fin], rtol=RTOL)          # observed ~1e-15
+    for g, want in zip(gpu_api.association_from_moments_batch(frames, na, k), probs):
+        np.testing.assert_allclose(g, want, rtol=RTOL, atol=1e-300)
+
+
 def test_oracle_getcovs(oracle):
     rng = np.random.default_rng(1)
     Q = rng.normal(size=(7, 4, 4)); Q = Q + Q.transpose(0, 2, 1)
