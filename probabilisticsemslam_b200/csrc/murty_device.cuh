@@ -17,6 +17,10 @@ constexpr unsigned FULL = 0xffffffffu;
 #ifndef PDA_MURTY_MINB
 #define PDA_MURTY_MINB 6
 #endif
+// warps per CTA of the throughput kernel (resident warps per SM = PDA_MURTY_MINB * PDA_MURTY_WPC)
+#ifndef PDA_MURTY_WPC
+#define PDA_MURTY_WPC 4
+#endif
 
 struct __align__(16) HeapEntry {
     double gain;

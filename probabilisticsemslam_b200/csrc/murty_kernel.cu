@@ -205,7 +205,7 @@ __device__ __forceinline__ WarpSmem carve(unsigned char* base, const MurtyGeomet
 }
 
 template <int R>
-__global__ void __launch_bounds__(128, PDA_MURTY_MINB) murty_kernel(const MurtyArgs a) {
+__global__ void __launch_bounds__(32 * PDA_MURTY_WPC, PDA_MURTY_MINB) murty_kernel(const MurtyArgs a) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -332,7 +332,7 @@ int murty_geometry(int32_t k, int32_t maxNumRow, int32_t maxNumCol, bool weights
     g->pCap = weights ? round_up(maxNumCol * maxNumRow, 2) : 0;
     const int baseSmem = round_up(8 * (g->cCap + g->pCap + 2 * D) + 3 * 2 * D, 16);
     // leftover shared memory (at the warps per SM the register budget allows) holds the top of the heap
-    const int budget = (227 * 1024 - PDA_MURTY_MINB * 1024) / (4 * PDA_MURTY_MINB);
+    const int budget = (227 * 1024 - PDA_MURTY_MINB * 1024) / (PDA_MURTY_WPC * PDA_MURTY_MINB);
     int topCap = budget > baseSmem ? (budget - baseSmem) / (int)sizeof(HeapEntry) : 0;
     if (topCap > g->maxNodes) topCap = g->maxNodes;
     if (topCap < 3) topCap = 0;
@@ -342,7 +342,7 @@ int murty_geometry(int32_t k, int32_t maxNumRow, int32_t maxNumCol, bool weights
     if (g->smemPerWarp > dev.maxSmemOptin)
         return fail(PDA_ERR_UNSUPPORTED, "murty: a %d x %d problem needs %d B of shared memory per warp (limit %d)",
                     maxNumRow, maxNumCol, g->smemPerWarp, dev.maxSmemOptin);
-    int wpc = 4;
+    int wpc = PDA_MURTY_WPC;
     while (wpc > 1 && wpc * g->smemPerWarp > dev.maxSmemOptin) wpc >>= 1;
     g->warpsPerCta = wpc;
     // resident CTAs per SM, as the occupancy calculator sees this instantiation (registers, shared memory)
