@@ -7,7 +7,7 @@ import numpy as np
 from probabilisticsemslam_b200 import api, synth
 from oracle.loader import load_oracle, load_reference, reference_available
 
-N, K, CHUNK = int(os.environ.get("FULL_N", "100000")), 200, 10000
+N, K, CHUNK = int(os.environ.get("FULL_N", "100000")), int(os.environ.get("FULL_K", "200")), int(os.environ.get("FULL_CHUNK", "10000"))
 chk, kind = (load_reference("strict"), "reference (oracle/_ref strict build)") if reference_available("strict") else (load_oracle(), "oracle restatement")
 bad_lists = bad_gain = bad_found = 0
 worst_w = 0.0
