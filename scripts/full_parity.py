@@ -14,7 +14,7 @@ worst_w = 0.0
 hyps = 0
 t0 = time.time()
 for first in range(0, N, CHUNK):
-    pb = synth.g1_dense(min(CHUNK, N - first), first=first)
+    pb = synth.g1_dense(min(CHUNK, N - first), first=first, integer=bool(int(os.environ.get("FULL_INT", "0"))))  # FULL_INT=1: exact-tie stress
     got = api.murty_batch(pb, K, weight_mode=api.WEIGHTS_GATED)
     want = chk.batch(pb, K, threads=os.cpu_count(), want_probs=True, want_lists=True)
     bad_found += int(np.count_nonzero(got.n_found != want["n_found"]))
@@ -32,6 +32,6 @@ for first in range(0, N, CHUNK):
     hyps += int(want["n_found"].sum())
     d = np.abs(got.probs - want["probs"]) / np.maximum(np.abs(want["probs"]), 1e-300)
     worst_w = max(worst_w, float(np.max(np.where(want["probs"] == got.probs, 0.0, d))))
-print(json.dumps({"problems": N, "k": K, "hypotheses_compared": hyps, "checker": kind, "problems_with_different_nFound": bad_found,
+print(json.dumps({"problems": N, "k": K, "integer_costs": bool(int(os.environ.get("FULL_INT", "0"))), "hypotheses_compared": hyps, "checker": kind, "problems_with_different_nFound": bad_found,
                   "problems_with_different_lists": bad_lists, "gains_with_different_bits": bad_gain,
                   "worst_relative_weight_difference": worst_w, "seconds": round(time.time() - t0, 1)}))
