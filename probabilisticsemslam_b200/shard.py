@@ -80,6 +80,42 @@ def sharded_assignment_prob(pb: ProblemBatch, k: int, *, compute: Callable | Non
     return np.concatenate([recv[r][:counts[r]].cpu().numpy() for r in range(world)])
 
 
+def sharded_association_from_moments(frames, nonassign: float, k: int, *, compute: Callable | None = None, group=None):
+    """getAssignmentProbs (assignment.cpp:38-74) for a list of frames -- (land_mean, land_cov, meas_mean, meas_cov) each,
+    e.g. the frames x window frames of a sliding-window update -- split across the ranks of `group`: rank r builds the
+    cost matrices of its contiguous slice on its GPU and runs the association pipeline there; one all_gather of the
+    variable-length weight vectors at the end, no other exchange.  Returns the list of (nM, nL+1) tables on every rank.
+    `compute(frames, nonassign, k) -> list of tables` defaults to the CUDA pipeline."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    lo, hi = shard_bounds(len(frames), world, rank)
+    if compute is None:
+        from . import api
+        compute = lambda fr, na, kk: api.association_from_moments_batch(fr, na, kk, device=torch.cuda.current_device())  # noqa: E731
+    shapes = [(int(np.asarray(f[2]).reshape(-1, 3).shape[0]), int(np.asarray(f[0]).reshape(-1, 3).shape[0]) + 1) for f in frames]
+    local_tabs = compute(frames[lo:hi], nonassign, k) if hi > lo else []
+    local = np.concatenate([np.asarray(t, np.float64).reshape(-1) for t in local_tabs]) if local_tabs else np.zeros(0)
+    if world > 1:
+        counts = [sum(m * w for m, w in shapes[slice(*shard_bounds(len(frames), world, r))]) for r in range(world)]
+        backend = dist.get_backend(group)
+        dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+        width = max(counts) if counts else 0
+        send = torch.zeros(width, dtype=torch.float64, device=dev)
+        send[:local.size] = torch.from_numpy(local).to(dev)
+        recv = [torch.zeros(width, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(recv, send, group=group)
+        flat = np.concatenate([recv[r][:counts[r]].cpu().numpy() for r in range(world)])
+    else:
+        flat = local
+    out, o = [], 0
+    for m, w in shapes:
+        out.append(flat[o:o + m * w].reshape(m, w))
+        o += m * w
+    return out
+
+
 def sharded_permanent(a: np.ndarray, *, partial: Callable | None = None, group=None) -> float:
     """Exact permanent of ONE square matrix with the Gray range split over the ranks of `group`
     (BASELINE.json configs[4]).  `partial(a, begin, end) -> (hi, lo)`."""

@@ -46,9 +46,13 @@ def _worker(rank, world, port, out):
         probs = shard.sharded_assignment_prob(pb, 40, compute=cpu)
         a = synth.dense_square(1, 9, first=3)[0].reshape(9, 9, order="F")
         perm = shard.sharded_permanent(a, partial=_nw_partial)
+        frames = synth.quadric_frames(7, nL=6, first=40)     # 7 frames: uneven split, ragged tables
+        cpu_frames = lambda fr, na, k: [orc.association_from_moments(*f, na, k) for f in fr]  # noqa: E731
+        tabs = shard.sharded_association_from_moments(frames, 10.0, 30, compute=cpu_frames)
         if rank == 0:
             np.save(out + ".probs.npy", probs)
             np.save(out + ".perm.npy", np.array([perm]))
+            np.save(out + ".tabs.npy", np.concatenate([t.reshape(-1) for t in tabs]))
     finally:
         dist.destroy_process_group()
 
@@ -62,6 +66,9 @@ def test_sharded_paths_match_single_process(tmp_path, oracle, world):
     np.testing.assert_array_equal(np.load(out + ".probs.npy"), want)      # same per-problem code, only re-assembled
     a = synth.dense_square(1, 9, first=3)[0].reshape(9, 9, order="F")
     np.testing.assert_allclose(np.load(out + ".perm.npy")[0], oracle.permanent_exact_square(a)[0], rtol=1e-12)
+    frames = synth.quadric_frames(7, nL=6, first=40)
+    want_tabs = np.concatenate([oracle.association_from_moments(*f, 10.0, 30).reshape(-1) for f in frames])
+    np.testing.assert_array_equal(np.load(out + ".tabs.npy"), want_tabs)
 
 
 def test_shard_bounds_cover_everything_once():
