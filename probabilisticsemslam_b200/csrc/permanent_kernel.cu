@@ -75,6 +75,13 @@ struct PermArgs {
     dd* partial;        // [nMats * ctasPerMat]
 };
 
+// Leading dimension of the matrix in shared memory.  When the threads of a warp flip DIFFERENT columns (the first
+// index of every aligned chunk) each lane reads column k at k*LD + j; with LD == NP the columns of a 24-row matrix
+// start only two distinct 128-byte phases apart and those reads serialise (ncu: a third of all shared-memory
+// wavefronts of the kernel were bank conflicts).  LD*8 bytes == an odd multiple of 16 modulo 128 spreads eight
+// consecutive columns over all eight 16-byte slots of a 128-byte line.
+__host__ __device__ constexpr int perm_ld(int np) { return ((np + 2) / 2) % 2 ? np + 2 : np + 4; }
+
 // Walks Gray indices [i0, i1) of the NW sum: seeds x for the subset gray(i0), adds its term, then steps.
 // Correct for ANY i0, i1; the column index ctz(i) is warp-uniform whenever it is below log2(chunk).
 template <int NP>
@@ -87,7 +94,7 @@ __device__ __forceinline__ dd walk_range(const double* __restrict__ sA, const do
     while (g) {
         const int b = __ffsll((long long)g) - 1;
         g &= g - 1;
-        const double* col = sA + b * NP;
+        const double* col = sA + b * perm_ld(NP);
 #pragma unroll
         for (int j = 0; j < NP; j += 2) {
             const double2 a = *reinterpret_cast<const double2*>(col + j);
@@ -113,7 +120,7 @@ __device__ __forceinline__ dd walk_range(const double* __restrict__ sA, const do
         const int k = __ffsll((long long)i) - 1;  // the bit in which gray(i) and gray(i-1) differ
         const unsigned long long gray = i ^ (i >> 1);
         const double s = ((gray >> k) & 1ULL) ? 1.0 : -1.0;
-        const double* col = sA + k * NP;
+        const double* col = sA + k * perm_ld(NP);
         double p[PERM_CHAINS];
 #pragma unroll
         for (int c = 0; c < PERM_CHAINS; ++c) p[c] = 1.0;
@@ -156,7 +163,7 @@ __device__ __forceinline__ dd walk_range_c0(const double* __restrict__ sA, const
     while (g) {
         const int b = __ffsll((long long)g) - 1;
         g &= g - 1;
-        const double* col = sA + b * NP;
+        const double* col = sA + b * perm_ld(NP);
 #pragma unroll
         for (int j = 0; j < NP; j += 2) {
             const double2 a = *reinterpret_cast<const double2*>(col + j);
@@ -201,7 +208,7 @@ __device__ __forceinline__ dd walk_range_c0(const double* __restrict__ sA, const
         if (ie < i1) {  // even index: column ctz(ie) >= 1 from shared memory
             const int k = __ffsll((long long)ie) - 1;
             const double s = (((ie ^ (ie >> 1)) >> k) & 1ULL) ? 1.0 : -1.0;
-            const double* col = sA + k * NP;
+            const double* col = sA + k * perm_ld(NP);
             double p[PERM_CHAINS];
 #pragma unroll
             for (int c = 0; c < PERM_CHAINS; ++c) p[c] = 1.0;
@@ -246,9 +253,10 @@ __global__ void __launch_bounds__(PERM_THREADS, perm_min_blocks(NP)) perm_kernel
     const int slot = tid / tpm, t = tid % tpm, slots = PERM_THREADS / tpm;
     const int64_t m = (int64_t)blockIdx.y * slots + slot;
     const int cta = blockIdx.x;
-    const int slotDoubles = NP * a.maxN + NP;
+    constexpr int LD = perm_ld(NP);
+    const int slotDoubles = LD * a.maxN + NP;
     double* sA = smemD + (size_t)slot * slotDoubles;
-    double* sBase = sA + NP * a.maxN;
+    double* sBase = sA + LD * a.maxN;
     const bool live = m < a.nMats;
     const int rows = live ? a.rows[m] : 0, cols = live ? a.cols[m] : 0;
     const int n = rows > cols ? rows : cols;
@@ -260,7 +268,7 @@ __global__ void __launch_bounds__(PERM_THREADS, perm_min_blocks(NP)) perm_kernel
             const int j = e % NP, k = e / NP;
             double val = 0.0;
             if (j < n) val = (j < rows && k < cols) ? A[j + (size_t)k * rows] : 1.0;
-            sA[e] = val;
+            sA[j + k * LD] = val;
         }
     }
     __syncthreads();
@@ -268,8 +276,8 @@ __global__ void __launch_bounds__(PERM_THREADS, perm_min_blocks(NP)) perm_kernel
         double b = 1.0;  // padded rows keep x == 1 forever
         if (t < n) {
             double rs = 0.0;
-            for (int k = 0; k < n; ++k) rs += sA[t + k * NP];
-            b = sA[t + (n - 1) * NP] - rs / 2;  // nwPerm.cpp:289
+            for (int k = 0; k < n; ++k) rs += sA[t + k * LD];
+            b = sA[t + (n - 1) * LD] - rs / 2;  // nwPerm.cpp:289
         }
         sBase[t] = b;
     }
@@ -348,7 +356,7 @@ __global__ void perm_finalize_kernel(const PermArgs a, double* __restrict__ out,
 template <int NP>
 int launch_np(const PermArgs& a, cudaStream_t stream) {
     const int slots = PERM_THREADS / a.threadsPerMat;
-    const size_t smem = (size_t)slots * (NP * a.maxN + NP) * sizeof(double);
+    const size_t smem = (size_t)slots * (perm_ld(NP) * a.maxN + NP) * sizeof(double);
     PDA_CUDA_TRY(cudaFuncSetAttribute(perm_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)a.ctasPerMat, (unsigned)((a.nMats + slots - 1) / slots));
     perm_kernel<NP><<<grid, PERM_THREADS, smem, stream>>>(a);
