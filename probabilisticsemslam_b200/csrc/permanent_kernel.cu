@@ -236,12 +236,93 @@ __device__ __forceinline__ dd walk_range_c0(const double* __restrict__ sA, const
     return r;
 }
 
+// Small matrices: columns 0 AND 1 in registers.  Column 1 flips at every index == 2 (mod 4), so three steps out of
+// four then need no shared-memory read.  Requires i0 == 0 (mod 4) and i1 - i0 a multiple of 4 (ranges are chunk aligned
+// with chunk >= 4 whenever this variant is selected).
+template <int NP>
+__device__ __forceinline__ dd walk_range_c01(const double* __restrict__ sA, const double* __restrict__ sBase,
+                                             const unsigned long long i0, const unsigned long long i1) {
+    double x[NP], c0[NP], c1[NP];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) { x[j] = sBase[j]; c0[j] = sA[j]; c1[j] = sA[perm_ld(NP) + j]; }
+    unsigned long long g = i0 ^ (i0 >> 1);
+    while (g) {
+        const int b = __ffsll((long long)g) - 1;
+        g &= g - 1;
+        const double* col = sA + b * perm_ld(NP);
+#pragma unroll
+        for (int j = 0; j < NP; j += 2) {
+            const double2 a = *reinterpret_cast<const double2*>(col + j);
+            x[j] += a.x;
+            x[j + 1] += a.y;
+        }
+    }
+    auto product = [&]() {
+        double p[PERM_CHAINS];
+#pragma unroll
+        for (int c = 0; c < PERM_CHAINS; ++c) p[c] = 1.0;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) p[j % PERM_CHAINS] *= x[j];
+#pragma unroll
+        for (int w = PERM_CHAINS / 2; w >= 1; w >>= 1)
+#pragma unroll
+            for (int c = 0; c < w; ++c) p[c] *= p[c + w];
+        return p[0];
+    };
+    double hi = product(), lo = 0.0;  // i0 is even: sign +
+    auto add = [&](double term) {
+        double s2, e;
+        two_sum(hi, term, s2, e);
+        hi = s2;
+        lo += e;
+    };
+    for (unsigned long long i = i0; i < i1; i += 4) {
+        if (i != i0) {  // index i == 0 (mod 4): column ctz(i) >= 2 from shared memory
+            const int k = __ffsll((long long)i) - 1;
+            const double s = (((i ^ (i >> 1)) >> k) & 1ULL) ? 1.0 : -1.0;
+            const double* col = sA + k * perm_ld(NP);
+#pragma unroll
+            for (int j = 0; j < NP; j += 2) {
+                const double2 a = *reinterpret_cast<const double2*>(col + j);
+                x[j] = fma(s, a.x, x[j]);
+                x[j + 1] = fma(s, a.y, x[j + 1]);
+            }
+            add(product());
+        }
+        {   // i + 1 (odd): column 0; gray bit 0 = 1 ^ bit 1 of the index = 1  -> +
+#pragma unroll
+            for (int j = 0; j < NP; ++j) x[j] += c0[j];
+            add(-product());
+        }
+        {   // i + 2: column 1; gray bit 1 = 1 ^ bit 2 of the index
+            const double s = ((i >> 2) & 1ULL) ? -1.0 : 1.0;
+#pragma unroll
+            for (int j = 0; j < NP; ++j) x[j] = fma(s, c1[j], x[j]);
+            add(product());
+        }
+        {   // i + 3 (odd): column 0; gray bit 0 = 1 ^ bit 1 = 0  -> -
+#pragma unroll
+            for (int j = 0; j < NP; ++j) x[j] -= c0[j];
+            add(-product());
+        }
+    }
+    dd r;
+    r.hi = hi;
+    r.lo = lo;
+    return r;
+}
+
 #ifndef PERM_C0_MAX
 #define PERM_C0_MAX 32
 #endif
+#ifndef PERM_C01_MAX
+#define PERM_C01_MAX 16
+#endif
+__host__ __device__ constexpr bool perm_cache01(int np) { return np <= PERM_C01_MAX; }
 __host__ __device__ constexpr bool perm_cache0(int np) { return np <= PERM_C0_MAX; }
 // resident CTAs per SM the register allocator must leave room for
 __host__ __device__ constexpr int perm_min_blocks(int np) {
+    if (perm_cache01(np)) return np <= 8 ? 4 : 2;
     return perm_cache0(np) ? (np <= 12 ? 4 : (np <= 16 ? 3 : 2)) : (np <= 16 ? 4 : (np <= 24 ? 3 : 2));
 }
 
@@ -297,7 +378,8 @@ __global__ void __launch_bounds__(PERM_THREADS, perm_min_blocks(NP)) perm_kernel
         unsigned long long lo = begin + g * per * chunk, hi = lo + per * chunk;
         if (hi > end) hi = end;
         if (g * per < nChunks && lo < hi) {
-            if (perm_cache0(NP) && (lo & 1ULL) == 0) acc = walk_range_c0<NP>(sA, sBase, lo, hi);
+            if (perm_cache01(NP) && (lo & 3ULL) == 0 && ((hi - lo) & 3ULL) == 0) acc = walk_range_c01<NP>(sA, sBase, lo, hi);
+            else if (perm_cache0(NP) && (lo & 1ULL) == 0) acc = walk_range_c0<NP>(sA, sBase, lo, hi);
             else acc = walk_range<NP>(sA, sBase, lo, hi);
         }
     }
