@@ -111,11 +111,13 @@ int pda_device_count(void) {
 
 // If `p` is page-locked host memory that the device can address (cudaHostAlloc / cudaHostRegister under unified
 // addressing), returns the device-side alias, else NULL.
-static void* mapped_alias(const void* p) {
+static void* mapped_alias(const void* p, int device) {
     if (!p) return nullptr;
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
-    return (at.type == cudaMemoryTypeHost) ? at.devicePointer : nullptr;
+    // page-locked by a context of THIS device (memory pinned for another device's context is only guaranteed to be
+    // addressable there unless it was allocated portable: take the copying path for it)
+    return (at.type == cudaMemoryTypeHost && at.device == device) ? at.devicePointer : nullptr;
 }
 
 // ---------------------------------------------------------------------------------------- Murty
@@ -271,8 +273,8 @@ int pda_murty_batch_host(const double* costs, const int64_t* costOff, const int3
     // Page-locked caller buffers are used in place: a warp reads its 2.4 KB cost matrix over PCIe once when it takes
     // the problem and writes the weight table when it is done, so both transfers hide under ~1.6 ms of computing per
     // problem instead of standing in front of and behind the kernel (161 MB in + 136 MB out per 100 000 problems).
-    double* const costsDev = static_cast<double*>(mapped_alias(costs));
-    double* const probsDev = weightMode ? static_cast<double*>(mapped_alias(probs)) : nullptr;
+    double* const costsDev = static_cast<double*>(mapped_alias(costs, device));
+    double* const probsDev = weightMode ? static_cast<double*>(mapped_alias(probs, device)) : nullptr;
     Stage st(device);
     const size_t oCost = st.reserve(costsDev ? 0 : nCost * 8), oCostOff = st.reserve(n * 8), oNR = st.reserve(n * 4), oNC = st.reserve(n * 4);
     const size_t oR4c = st.reserve(nR4c * 8), oR4cOff = st.reserve(n * 8), oC4r = st.reserve(nC4r * 8), oC4rOff = st.reserve(n * 8);
