@@ -143,3 +143,33 @@ def test_kbest_marginals_approach_brute_force(oracle):
         if f"bf_{p}" in z:
             assert np.max(np.abs(z[f"k200_{p}"] - z[f"bf_{p}"])) < 0.1
             assert np.max(np.abs(z[f"pp_{p}"] - z[f"bf_{p}"])) < 1e-6
+
+
+def test_kbest_is_the_sorted_list_of_all_assignments(oracle):
+    """Independent of the reference: on tiny problems the k-best list must be exactly the cheapest feasible assignments
+    (every detection to a distinct landmark or to its own missed-detection row), in non-decreasing order of cost, each
+    listed once, with gain == the sum of the chosen entries."""
+    import itertools
+    rng = np.random.default_rng(77)
+    for trial in range(60):
+        nL, nM = int(rng.integers(0, 5)), int(rng.integers(1, 4))
+        C = np.full((nL + nM, nM), np.inf)
+        C[:nL, :] = np.where(rng.random((nL, nM)) < 0.8, rng.uniform(0, 20, size=(nL, nM)), np.inf)
+        C[nL + np.arange(nM), np.arange(nM)] = 10.0
+        every = []
+        for rows in itertools.permutations(range(nL + nM), nM):
+            cost = sum(C[r, c] for c, r in enumerate(rows))
+            if np.isfinite(cost):
+                every.append((cost, rows))
+        every.sort(key=lambda t: t[0])
+        k = 40
+        n, r4c, c4r, g = oracle.kbest2d(k, C)
+        assert n == min(k, len(every)), (trial, n, len(every))
+        np.testing.assert_allclose(g[:n], [e[0] for e in every[:n]], rtol=1e-12, atol=1e-12)
+        seen = set()
+        for i in range(n):
+            rows = tuple(int(x) for x in r4c[i])
+            assert rows not in seen
+            seen.add(rows)
+            assert abs(sum(C[r, c] for c, r in enumerate(rows)) - g[i]) <= 1e-12 * max(1.0, abs(g[i]))
+            assert all(c4r[i][r] == c for c, r in enumerate(rows))
