@@ -76,15 +76,19 @@ double pda_diag_dfma_tflops(void);
  */
 int64_t pda_murty_workspace_bytes(int64_t nProblems, int32_t k, int32_t maxNumRow, int32_t maxNumCol);
 
-/* Two kernels stand behind pda_murty_batch, with bit-identical results: one WARP per problem (throughput: large
- * batches) and one CTA per problem (latency: a node's Murty split is computed by 16 warps before the node reaches
- * the top of the queue and committed in the reference's order; taken for batches of up to 4 problems per SM with at
- * most 16 detections each -- the per-frame call of the SLAM loop, system.cpp:268).  PDA_MURTY_PATH_AUTO picks by
- * batch size; the other two values force a kernel (tests, measurements).  Process-wide; returns the previous value.
- * Set it before sizing the workspace. */
+/* Three kernels stand behind pda_murty_batch, with bit-identical results: one WARP per problem, exact (the
+ * reference's heap order replayed; always right), one WARP per problem, FAST (large batches: hypotheses that provably
+ * cannot be among the k best are abandoned early and the open list is a warp-parallel queue; a problem in which two
+ * open hypotheses have bit-equal gains is handed to the exact kernel, which runs right behind it), and one CTA per
+ * problem (latency: a node's Murty split is computed by 16 warps before the node reaches the top of the queue and
+ * committed in the reference's order; taken for batches of up to 4 problems per SM with at most 16 detections each
+ * -- the per-frame call of the SLAM loop, system.cpp:268).  PDA_MURTY_PATH_AUTO picks by batch size (CTA for small
+ * batches, else FAST when the geometry admits it, else WARP); the other values force a kernel (tests, measurements).
+ * Process-wide; returns the previous value.  Set it before sizing the workspace. */
 #define PDA_MURTY_PATH_AUTO 0
 #define PDA_MURTY_PATH_WARP 1
 #define PDA_MURTY_PATH_CTA 2
+#define PDA_MURTY_PATH_FAST 3
 int pda_murty_set_path(int32_t path);
 
 int pda_murty_batch(const double* costs, const int64_t* costOff, const int32_t* numRow, const int32_t* numCol,

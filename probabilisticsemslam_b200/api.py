@@ -26,7 +26,7 @@ WEIGHTS_NONE, WEIGHTS_GATED, WEIGHTS_UNGATED = 0, 1, 2
 GATE = 42.0  # assignment.cpp:9
 
 
-MURTY_PATHS = {"auto": 0, "warp": 1, "cta": 2}
+MURTY_PATHS = {"auto": 0, "warp": 1, "cta": 2, "fast": 3}
 
 
 def set_murty_path(path: str) -> str:

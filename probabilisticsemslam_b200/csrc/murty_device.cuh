@@ -17,6 +17,11 @@ constexpr unsigned FULL = 0xffffffffu;
 #ifndef PDA_MURTY_MINB
 #define PDA_MURTY_MINB 6
 #endif
+// the same for the pruning kernel (murty_kernel<R, true>): measured 6 -> 5 CTAs per SM (102 registers instead of 80)
+// +9 %: at 80 registers the compiler re-derives the masked row duals and the shared-memory addresses in every Dijkstra step
+#ifndef PDA_FAST_MINB
+#define PDA_FAST_MINB 5
+#endif
 // warps per CTA of the throughput kernel (resident warps per SM = PDA_MURTY_MINB * PDA_MURTY_WPC)
 #ifndef PDA_MURTY_WPC
 #define PDA_MURTY_WPC 4
@@ -98,6 +103,13 @@ __device__ __forceinline__ void relax(const double* __restrict__ Ccol, const int
 }
 
 constexpr int NAN_HI = 0x7ff80000;  // high word of the NaN that marks a scanned row's candidate
+
+#ifdef PDA_FAST_STATS
+__device__ unsigned long long g_augStats[8];  // argmins, ff tried, ff applied, loop trips, flip hops, searches, real relax, pad relax
+#define PDA_ASTAT(i) do { if (lane == 0) atomicAdd(&g_augStats[i], 1ULL); } while (0)
+#else
+#define PDA_ASTAT(i) do { } while (0)
+#endif
 
 // Fast-forward over the reference's no-op hops.
 //
@@ -188,10 +200,19 @@ __device__ __forceinline__ int fast_forward(const int numColReal, const WarpSmem
 // children against it; the root LAP republishes after every column.  uRowPar, when given, is the start node's "u of the
 // column each row is paired with", computed once per split (the freed row's entry is stale there, but a free row is a
 // stopper and never consulted).
-template <int R>
-__device__ __forceinline__ bool augment_from(const int startCol, const int numColReal, const int ld,
-                                             const WarpSmem& sm, Node<R>& nd, const unsigned scanBits,
-                                             const unsigned forbBits, const int lane, const double* uRowPar = nullptr) {
+//
+// LIMIT (the pruning fast path, murty_kernel.cu): the search is abandoned -- return 2, working node untouched -- as
+// soon as the distance of the row about to be scanned exceeds `limit`.  Distances only grow along a Dijkstra search
+// and the finished child's gain is the parent's gain plus the final distance (up to rounding, which the caller's
+// margin absorbs), so such a child cannot be among the hypotheses still wanted.
+// Returns 0 = augmented, 1 = infeasible, 2 = abandoned.
+// FF = false leaves fast_forward out (the root LAP: 3 % of the work, and one inlined copy less of the largest routine
+// keeps the kernel inside the instruction cache); the search then simply takes the reference's steps one by one.
+template <int R, bool LIMIT = false, bool FF = true>
+__device__ __forceinline__ int augment_from(const int startCol, const int numColReal, const int ld,
+                                            const WarpSmem& sm, Node<R>& nd, const unsigned scanBits,
+                                            const unsigned forbBits, const int lane, const double* uRowPar = nullptr,
+                                            const double limit = __builtin_huge_val()) {
     double cand[R], vEff[R];
     int pred[R];
 #pragma unroll
@@ -213,14 +234,16 @@ __device__ __forceinline__ bool augment_from(const int startCol, const int numCo
     // u of the column each owned row is paired with (only rows paired with padding columns use it)
     double uRow[R];
 #pragma unroll
-    for (int s = 0; s < R; ++s) uRow[s] = uRowPar ? uRowPar[s] : ((nd.c4r[s] >= 0) ? sm.u[nd.c4r[s]] : 0.0);
+    for (int s = 0; s < R; ++s) uRow[s] = !FF ? 0.0 : (uRowPar ? uRowPar[s] : ((nd.c4r[s] >= 0) ? sm.u[nd.c4r[s]] : 0.0));
     bool padPrev = cur >= numColReal;  // the last relaxation came from a padding column
     for (;;) {
         int closest = 0;
         int ff = 0;
-        if (padPrev) ff = fast_forward<R>(numColReal, sm, nd, vEff, uRow, cand, closest, delta, lane);
-        if (ff == 2) return true;
+        PDA_ASTAT(3);
+        if (FF && padPrev) { PDA_ASTAT(1); ff = fast_forward<R>(numColReal, sm, nd, vEff, uRow, cand, closest, delta, lane); if (ff) PDA_ASTAT(2); }
+        if (ff == 2) return 1;
         if (ff == 0) {
+            PDA_ASTAT(0);
             // lane-local first minimum (lower slot = lower row wins ties; NaN = already scanned), then the warp arg-min
             double best = cand[0];
             int bs = 0;
@@ -229,12 +252,13 @@ __device__ __forceinline__ bool augment_from(const int startCol, const int numCo
             unsigned khi, klo;
             to_key(best, khi, klo);
             const unsigned mhi = __reduce_min_sync(FULL, khi);
-            if (mhi >= KEY_INF_HI) return true;  // minVal == +inf (:197, :327): nothing finite is left
+            if (mhi >= KEY_INF_HI) return 1;  // minVal == +inf (:197, :327): nothing finite is left
             const unsigned mlo = __reduce_min_sync(FULL, (khi == mhi) ? klo : 0xffffffffu);
             const bool win = (khi == mhi) && (klo == mlo);
             closest = (int)__reduce_min_sync(FULL, win ? (unsigned)(lane + 32 * bs) : 0xffffu);
             delta = from_key(mhi, mlo);
         }
+        if (LIMIT && delta > limit) return 2;
         if (lane == 0) sm.spc[closest] = delta;
 #pragma unroll
         for (int s = 0; s < R; ++s)
@@ -244,9 +268,10 @@ __device__ __forceinline__ bool augment_from(const int startCol, const int numCo
         cur = (int)next;
         padPrev = cur >= numColReal;
         const double ucur = sm.u[cur];
-        if (padPrev) relax<R, false>(nullptr, ld, delta, ucur, vEff, cur, cand, pred, lane);
-        else relax<R, true>(sm.C + cur * ld, ld, delta, ucur, vEff, cur, cand, pred, lane);
+        if (padPrev) { PDA_ASTAT(7); relax<R, false>(nullptr, ld, delta, ucur, vEff, cur, cand, pred, lane); }
+        else { PDA_ASTAT(6); relax<R, true>(sm.C + cur * ld, ld, delta, ucur, vEff, cur, cand, pred, lane); }
     }
+    PDA_ASTAT(5);
 
     // duals, using row4col as it was before the flip (:92-106).  A column other than startCol was scanned
     // exactly when the row it is paired with was scanned (the sink row is unpaired).
@@ -274,6 +299,7 @@ __device__ __forceinline__ bool augment_from(const int startCol, const int numCo
     // flip along the predecessor chain (:108-116); sm.r4c still holds the pre-flip pairing
     int r = sink, c;
     do {
+        PDA_ASTAT(4);
         c = sm.pred[r];
         const int h = sm.r4c[c];
 #pragma unroll
@@ -284,7 +310,7 @@ __device__ __forceinline__ bool augment_from(const int startCol, const int numCo
         r = h;
     } while (c != startCol);
     __syncwarp();  // the chain walk has read sm.pred / sm.r4c before anybody rewrites them
-    return false;
+    return 0;
 }
 
 // calcGain (:59-80): ascending column order, starting from 0.0.
@@ -376,6 +402,171 @@ __device__ __forceinline__ void heap_pop(const Heap& h, const int lenBefore) {
         }
         heap_sift_up4(h, hole, val);
     }
+}
+
+// ---- the open list of the pruning fast path ---------------------------------------------------------------
+// Used only while no two gains that matter are bit-equal (the caller hands the problem to the exact kernel the moment
+// a selection is not unique), so ANY correct priority queue pops in the reference's order and the libstdc++ layout
+// above is not needed.  That buys a structure a warp can work on with all its lanes:
+//   key[] / node[]  unsorted slots; a removed slot holds PQ_EMPTY until the next compaction
+//   gmin[g]         smallest key among slots 32g .. 32g+31
+// push   = append + one compare (lane 0);   take-min = arg-min over gmin, one 32-wide look at that group, new group
+// minimum from the keys already in registers: ~40 warp instructions whatever the size, against ~130 for a binary-heap
+// pop by a single lane.  Gains are >= +0.0, so their bit patterns order like the numbers.
+#ifndef PDA_PQ_UNROLL1
+#define PDA_PQ_UNROLL1 1
+#endif
+#if PDA_PQ_UNROLL1
+#define PDA_PQ_LOOP _Pragma("unroll 1")
+#else
+#define PDA_PQ_LOOP
+#endif
+#ifndef PDA_TIGHTEN_NOINLINE
+#define PDA_TIGHTEN_NOINLINE 0   // measured: a real call costs 13 % (reference parameters and caller-saved registers go through local memory)
+#endif
+#if PDA_TIGHTEN_NOINLINE
+#define PDA_TIGHTEN_INLINE __noinline__
+#else
+#define PDA_TIGHTEN_INLINE __forceinline__
+#endif
+constexpr unsigned long long PQ_EMPTY = ~0ULL;
+constexpr int PQ_SLACK = 8;  // surplus candidates that trigger the next tightening of the bound
+struct FastPQ {
+    unsigned long long* key;   // [cap]
+    int* node;                 // [cap]
+    unsigned long long* gmin;  // [cap / 32], shared memory
+    unsigned* hist;            // [32] scratch for pq_tighten (aliases sm.spc: never live during a search)
+    int cap;
+};
+__device__ __forceinline__ unsigned long long warp_min_u64(const unsigned long long x) {
+    const unsigned hi = (unsigned)(x >> 32), lo = (unsigned)x;
+    const unsigned mhi = __reduce_min_sync(FULL, hi);
+    const unsigned mlo = __reduce_min_sync(FULL, (hi == mhi) ? lo : 0xffffffffu);
+    return ((unsigned long long)mhi << 32) | mlo;
+}
+__device__ __forceinline__ unsigned long long warp_max_u64(const unsigned long long x) {
+    const unsigned hi = (unsigned)(x >> 32), lo = (unsigned)x;
+    const unsigned mhi = __reduce_max_sync(FULL, hi);
+    const unsigned mlo = __reduce_max_sync(FULL, (hi == mhi) ? lo : 0u);
+    return ((unsigned long long)mhi << 32) | mlo;
+}
+__device__ __forceinline__ void pq_push(const FastPQ& q, int& len, const double gain, const int node, const int lane) {
+    if (lane == 0) {
+        const unsigned long long kb = (unsigned long long)__double_as_longlong(gain);
+        q.key[len] = kb;
+        q.node[len] = node;
+        const int g = len >> 5;
+        if ((len & 31) == 0 || kb < q.gmin[g]) q.gmin[g] = kb;
+    }
+    len++;
+}
+// Removes the smallest entry (len > 0 and at least one live slot).  Returns true when that choice was NOT unique: some
+// other live entry has the same gain bits, and only the reference's heap mechanics can say which one goes first.
+__device__ __forceinline__ bool pq_take_min(const FastPQ& q, const int len, unsigned long long& keyOut, int& nodeOut,
+                                            const int lane) {
+    __syncwarp();
+    const int G = (len + 31) >> 5;
+    unsigned long long m = PQ_EMPTY;
+    int mg = 0;
+    bool dup = false;
+PDA_PQ_LOOP
+    for (int g = lane; g < G; g += 32) {
+        const unsigned long long x = q.gmin[g];
+        dup = dup || (x == m && x != PQ_EMPTY);
+        if (x < m) { m = x; mg = g; dup = false; }
+    }
+    const unsigned long long kmin = warp_min_u64(m);
+    const unsigned eq = __ballot_sync(FULL, m == kmin);
+    const int grp = __shfl_sync(FULL, mg, __ffs(eq) - 1);
+    bool tie = (__popc(eq) > 1) || (G > 32 && __any_sync(FULL, dup && m == kmin));
+    const int i = 32 * grp + lane;
+    const unsigned long long kk = (i < len) ? q.key[i] : PQ_EMPTY;
+    const unsigned eqi = __ballot_sync(FULL, kk == kmin);
+    tie = tie || (__popc(eqi) > 1);
+    const int w = __ffs(eqi) - 1;
+    nodeOut = q.node[32 * grp + w];
+    const unsigned long long rest = warp_min_u64((lane == w) ? PQ_EMPTY : kk);
+    if (lane == 0) { q.key[32 * grp + w] = PQ_EMPTY; q.gmin[grp] = rest; }
+    keyOut = kmin;
+    return tie;
+}
+// Lowers the pruning bound T and drops what it rules out.  Precondition: at least `m` live entries, m >= 1 = the
+// number of hypotheses still to be emitted; every live entry is <= T.  Afterwards T is (close to) the m-th smallest live
+// gain: the hypotheses already emitted plus m open ones at or below T exist, so nothing above T can be among the k
+// best.  One histogram pass over 32 equal buckets between the smallest and the largest live gain picks the bucket that
+// holds the m-th entry; its upper edge is the new bound (the count is re-checked with plain comparisons, so rounding
+// in the bucket arithmetic can only make the bound looser, never wrong).  Survivors are compacted to the front.
+__device__ PDA_TIGHTEN_INLINE void pq_tighten(const FastPQ& q, int& len, int& live, double& T, const int m, const int lane) {
+    __syncwarp();
+    const int S = (len + 31) >> 5;
+    unsigned long long lo = PQ_EMPTY, hi = 0ULL;
+PDA_PQ_LOOP
+    for (int s = 0; s < S; ++s) {
+        const int i = 32 * s + lane;
+        const unsigned long long kk = (i < len) ? q.key[i] : PQ_EMPTY;
+        if (kk != PQ_EMPTY) { lo = (kk < lo) ? kk : lo; hi = (kk > hi) ? kk : hi; }
+    }
+    lo = warp_min_u64(lo);
+    hi = warp_max_u64(hi);
+    const double dlo = __longlong_as_double((long long)lo), dhi = __longlong_as_double((long long)hi);
+    double Tn = dhi;
+    if (dhi > dlo) {
+        const double width = (dhi - dlo) * 0.03125;
+        const double inv = 1.0 / width;
+        q.hist[lane] = 0u;
+        __syncwarp();
+    PDA_PQ_LOOP
+    for (int s = 0; s < S; ++s) {
+            const int i = 32 * s + lane;
+            const unsigned long long kk = (i < len) ? q.key[i] : PQ_EMPTY;
+            if (kk != PQ_EMPTY) {
+                int b = (int)((__longlong_as_double((long long)kk) - dlo) * inv);
+                b = b > 31 ? 31 : (b < 0 ? 0 : b);
+                atomicAdd(&q.hist[b], 1u);
+            }
+        }
+        __syncwarp();
+        unsigned c = q.hist[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(FULL, c, o); if (lane >= o) c += y; }
+        const unsigned reach = __ballot_sync(FULL, c >= (unsigned)m);
+        const int bstar = __ffs(reach) - 1;
+        if (bstar >= 0 && bstar < 31) { Tn = dlo + (double)(bstar + 1) * width; Tn = (Tn > dhi) ? dhi : Tn; }
+        __syncwarp();  // hist is scratch of the next search from here on
+    }
+    unsigned long long tb = (unsigned long long)__double_as_longlong(Tn);
+    int cnt = 0;
+PDA_PQ_LOOP
+    for (int s = 0; s < S; ++s) {
+        const int i = 32 * s + lane;
+        const unsigned long long kk = (i < len) ? q.key[i] : PQ_EMPTY;
+        cnt += __popc(__ballot_sync(FULL, kk <= tb));
+    }
+    if (cnt < m) { tb = hi; Tn = dhi; }  // a bucket edge rounded the wrong way: keep every live entry
+    const unsigned below = (1u << lane) - 1u;
+    int out = 0;
+PDA_PQ_LOOP
+    for (int s = 0; s < S; ++s) {
+        const int i = 32 * s + lane;
+        const unsigned long long kk = (i < len) ? q.key[i] : PQ_EMPTY;
+        const int nn = (i < len) ? q.node[i] : 0;
+        const bool keep = kk <= tb;
+        const unsigned km = __ballot_sync(FULL, keep);
+        __syncwarp();  // every lane has read this slot before a survivor may be moved into it
+        if (keep) { const int d = out + __popc(km & below); q.key[d] = kk; q.node[d] = nn; }
+        out += __popc(km);
+    }
+    __syncwarp();
+    len = out;
+    live = out;
+    T = Tn;
+PDA_PQ_LOOP
+    for (int g = 0; 32 * g < out; ++g) {
+        const int i = 32 * g + lane;
+        const unsigned long long mn = warp_min_u64((i < out) ? q.key[i] : PQ_EMPTY);
+        if (lane == 0) q.gmin[g] = mn;
+    }
+    __syncwarp();
 }
 
 // ---- node arena -------------------------------------------------------------------------------------

@@ -24,14 +24,34 @@
 // enumeration order are bit-identical to an IEEE-strict build of the reference.
 // The heap replays libstdc++'s __push_heap / __adjust_heap so that exact gain ties
 // pop in the same order as std::priority_queue<pMurtyHyp> (shortestPathCPP.cpp:30-42).
+//
+// Two instantiations of the same enumeration:
+//   FAST = false  the exact kernel: the open list is the libstdc++ heap replay, every child is solved and kept.  Always
+//                 right, including the order of hypotheses with bit-equal gains.
+//   FAST = true   the pruning kernel, tried first on large batches.  (1) The open list is the warp-parallel FastPQ.
+//                 (2) Once `k` hypotheses are known to exist at or below a bound T (those already emitted plus open ones),
+//                 a child whose search distance pushes it past T is abandoned after its first arg-min and a finished
+//                 child above T is not stored: such hypotheses can never be emitted, and on the benchmark shape they are
+//                 a third of all children.  Both shortcuts are invisible in the output as long as the hypothesis chosen
+//                 next is unique; the moment it is not (two open entries with the same gain bits) the problem is
+//                 appended to a fallback list and redone from scratch by the exact kernel, which runs right behind on
+//                 the same stream over that list.  Continuous costs never tie; integer or 6-decimal costs do, and simply
+//                 take the exact kernel.
 #include "murty_device.cuh"
 
 namespace pda {
 namespace {
 
-template <int R>
+#ifdef PDA_FAST_STATS
+__device__ unsigned long long g_fastStats[8];  // children, abandoned, dropped at the end, kept, tighten calls, slots at tighten, pops
+#define PDA_STAT(i, v) do { if (lane == 0) atomicAdd(&g_fastStats[i], (unsigned long long)(v)); } while (0)
+#else
+#define PDA_STAT(i, v) do { } while (0)
+#endif
+
+template <int R, bool FAST>
 __device__ void solve_problem(const MurtyArgs& a, const long long p, const WarpSmem& sm, const Heap& heap,
-                              unsigned char* nodes, const int lane) {
+                              const FastPQ& pq, unsigned char* nodes, const int lane) {
     const int n = a.numRow[p], nc = a.numCol[p];
     const int D = a.geo.nodeDim;
     const bool wantW = a.weightMode != PDA_WEIGHTS_NONE;
@@ -70,7 +90,10 @@ __device__ void solve_problem(const MurtyArgs& a, const long long p, const WarpS
 #pragma unroll
     for (int s = 0; s < R; ++s) if (lane + 32 * s < n) allRows |= 1u << s;
     for (int c = 0; c < n; ++c) {
-        const bool stuck = augment_from<R>(c, nc, n, sm, nd, allRows, 0u, lane);
+#ifndef PDA_ROOT_FF
+#define PDA_ROOT_FF 1
+#endif
+        const bool stuck = augment_from<R, false, PDA_ROOT_FF != 0>(c, nc, n, sm, nd, allRows, 0u, lane);
         publish_cols<R>(sm, nd, lane);  // the next column starts from this solution
         if (stuck) {
             if (lane == 0) a.nFound[p] = 0;
@@ -104,14 +127,33 @@ __device__ void solve_problem(const MurtyArgs& a, const long long p, const WarpS
     double total = 0.0;
     if (wantW && nc > 1) add_weight<R>(a, sm, nd, nc, nL, gain0Out, gain0Out, total, lane);
 
-    int heapLen = 1;   // the root; its state is live in registers, slot 0 of the arena stays unused
+    int heapLen = FAST ? 0 : 1;   // exact: the root is the heap's only entry (its state is live in registers, slot 0 of
+                                  // the arena stays unused); fast: slots in use, the root never enters the list
     int nNodes = 1;
     int sweep = 1;
+    int live = 0;                 // fast: open entries (heapLen counts the removed slots as well until a compaction)
+    double T = CUDART_INF;        // fast: no hypothesis above T can be among the k best
+    int trig = 0;                 // fast: surplus of open entries over hypotheses still wanted that triggers pq_tighten
+    bool bail = false;
     for (; sweep < a.k; ++sweep) {
-        // ---- pop the node whose state we hold (it is the heap top) ---------------------------
-        if (lane == 0) heap_pop(heap, heapLen);
-        heapLen--;
-        __syncwarp();
+        double limit = CUDART_INF;
+        if (FAST) {
+            const int m = a.k - sweep;  // hypotheses still to be emitted: sweep .. k-1
+            if ((T == CUDART_INF) ? (live >= m) : (live - m >= trig)) {
+                PDA_STAT(4, 1); PDA_STAT(5, heapLen);
+                pq_tighten(pq, heapLen, live, T, m, lane);
+                trig = live - m + PQ_SLACK;
+            }
+            if (heapLen + nc > pq.cap) { bail = true; break; }
+            // children are compared with T through parent gain + search distance: 1e-7 relative is ~1e6 times the
+            // rounding that separates that sum from the child's calcGain value
+            limit = (T - gain) + 1e-7 * (T + 1.0);
+        } else {
+            // ---- pop the node whose state we hold (it is the heap top) -----------------------
+            if (lane == 0) heap_pop(heap, heapLen);
+            heapLen--;
+            __syncwarp();
+        }
 
         // ---- split (:455-532) --------------------------------------------------------------
         Node<R> par = nd;
@@ -138,36 +180,55 @@ __device__ void solve_problem(const MurtyArgs& a, const long long p, const WarpS
             }
             hideFirst = (c == a0) ? parForb : mine;  // first child inherits every constraint on the active column (:490)
             __syncwarp();
-            const bool infeasible = augment_from<R>(c, nc, n, sm, nd, inPar, hideFirst, lane, uRowPar);
+            const int stuck = augment_from<R, FAST>(c, nc, n, sm, nd, inPar, hideFirst, lane, uRowPar, limit);
+            if (FAST) { PDA_STAT(0, 1); if (stuck == 2) PDA_STAT(1, 1); }
 #pragma unroll
             for (int s = 0; s < R; ++s) if ((mine >> s) & 1u) sm.c4r[lane + 32 * s] = (unsigned short)c;  // the parent's pairing again
-            if (!infeasible) {
+            if (!stuck) {
                 const double g = path_gain_reg<R>(sm, nd, n, nc, lane);
-                const bool cut = cutting && (cutMax ? (g < cutoffGain) : (g > cutoffGain));
+                bool cut = cutting && (cutMax ? (g < cutoffGain) : (g > cutoffGain));
+                if (FAST) { if (!cut && g > T) PDA_STAT(2, 1); cut = cut || (g > T); }
                 if (!cut) {
+                    if (FAST) PDA_STAT(3, 1);
                     unsigned childForb = hideFirst;
 #pragma unroll
                     for (int s = 0; s < R; ++s) if (nd.c4r[s] == c) childForb |= 1u << s;  // the row column c ended up with (:362)
                     node_store<R>(nodes + (size_t)nNodes * a.geo.nodeStride, D, n, nd, childForb, c, lane);
-                    if (lane == 0) {
-                        HeapEntry e;
-                        e.gain = g; e.node = nNodes; e.pad = 0;
-                        heap_sift_up(heap, heapLen, e);
+                    if (FAST) {
+                        pq_push(pq, heapLen, g, nNodes, lane);
+                        live++;
+                    } else {
+                        if (lane == 0) {
+                            HeapEntry e;
+                            e.gain = g; e.node = nNodes; e.pad = 0;
+                            heap_sift_up(heap, heapLen, e);
+                        }
+                        heapLen++;
                     }
-                    heapLen++;
                     nNodes++;
                 }
             }
             inPar &= ~mine;  // column c is fixed from here on
         }
         __syncwarp();
-        if (heapLen == 0) break;
-
         // ---- the new top is hypothesis number `sweep` (:703-719) ---------------------------
-        const HeapEntry top = heap.get(0);
-        __syncwarp();  // every lane has read the top before lane 0 starts the next pop
-        gain = top.gain;
-        node_load<R>(nodes + (size_t)top.node * a.geo.nodeStride, D, n, nd, forb, activeCol, lane);
+        int topNode;
+        if (FAST) {
+            if (live == 0) break;
+            unsigned long long kb;
+            const bool tie = pq_take_min(pq, heapLen, kb, topNode, lane);
+            PDA_STAT(6, 1);
+            live--;
+            if (tie) { bail = true; break; }
+            gain = __longlong_as_double((long long)kb);
+        } else {
+            if (heapLen == 0) break;
+            const HeapEntry top = heap.get(0);
+            __syncwarp();  // every lane has read the top before lane 0 starts the next pop
+            gain = top.gain;
+            topNode = top.node;
+        }
+        node_load<R>(nodes + (size_t)topNode * a.geo.nodeStride, D, n, nd, forb, activeCol, lane);
         double gainOut;
         bool stop = false;
         if (!maximize) {
@@ -180,6 +241,10 @@ __device__ void solve_problem(const MurtyArgs& a, const long long p, const WarpS
         emit<R>(a, p, sweep, n, nc, nd, gainOut, lane);
         if (stop) break;
         if (wantW && nc > 1) add_weight<R>(a, sm, nd, nc, nL, gain0Out, gainOut, total, lane);
+    }
+    if (FAST && bail) {  // not decidable without the reference's heap order (or the list is full): the exact kernel redoes it
+        if (lane == 0) a.fallbackList[atomicAdd(a.fallbackCount, 1u)] = (int32_t)p;
+        return;
     }
     if (lane == 0) a.nFound[p] = sweep;
     if (wantW && nc > 1) {
@@ -204,26 +269,41 @@ __device__ __forceinline__ WarpSmem carve(unsigned char* base, const MurtyGeomet
     return sm;
 }
 
-template <int R>
-__global__ void __launch_bounds__(32 * PDA_MURTY_WPC, PDA_MURTY_MINB) murty_kernel(const MurtyArgs a) {
+template <int R, bool FAST>
+__global__ void __launch_bounds__(32 * PDA_MURTY_WPC, FAST ? PDA_FAST_MINB : PDA_MURTY_MINB) murty_kernel(const MurtyArgs a) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = blockIdx.x * (blockDim.x >> 5) + warp;
     if (gw >= a.nWarps) return;
-    const WarpSmem sm = carve(smemRaw + (size_t)warp * a.geo.smemPerWarp, a.geo);
+    const int smemPerWarp = FAST ? a.geo.fastSmemPerWarp : a.geo.smemPerWarp;
+    unsigned char* mySmem = smemRaw + (size_t)warp * smemPerWarp;
+    const WarpSmem sm = carve(mySmem, a.geo);
     unsigned char* arena = a.arena + (size_t)gw * a.geo.arenaStride;
     Heap heap;
     heap.deep = reinterpret_cast<HeapEntry*>(arena);
-    heap.top = reinterpret_cast<HeapEntry*>(smemRaw + (size_t)warp * a.geo.smemPerWarp + a.geo.heapTopOff);
+    heap.top = reinterpret_cast<HeapEntry*>(mySmem + a.geo.heapTopOff);
     heap.topCap = a.geo.heapTopCap;
+    FastPQ pq;
+    pq.cap = a.geo.pqCap;
+    pq.gmin = reinterpret_cast<unsigned long long*>(mySmem + a.geo.heapTopOff);
+    if (a.geo.pqInSmem) {
+        pq.key = pq.gmin + (a.geo.pqCap >> 5);
+        pq.node = reinterpret_cast<int*>(pq.key + a.geo.pqCap);
+    } else {  // the arena's heap region is free in this kernel
+        pq.key = reinterpret_cast<unsigned long long*>(arena);
+        pq.node = reinterpret_cast<int*>(pq.key + a.geo.pqCap);
+    }
+    pq.hist = reinterpret_cast<unsigned*>(sm.spc);
     unsigned char* nodes = arena + a.geo.heapBytes;
+    // the exact kernel, when it runs behind the fast one, takes its problem count from the fallback counter
+    const long long nProblems = a.nProblemsDev ? (long long)*a.nProblemsDev : a.nProblems;
     for (;;) {
         unsigned long long p = 0;
         if (lane == 0) p = atomicAdd(a.cursor, 1ULL);
         p = __shfl_sync(FULL, p, 0);
-        if ((long long)p >= a.nProblems) break;
+        if ((long long)p >= nProblems) break;
         if (a.order) p = (unsigned long long)a.order[p];  // most expensive problems first: a short tail
-        solve_problem<R>(a, (long long)p, sm, heap, nodes, lane);
+        solve_problem<R, FAST>(a, (long long)p, sm, heap, pq, nodes, lane);
         __syncwarp();
     }
 }
@@ -312,6 +392,29 @@ __global__ void lap_kernel(const LapArgs a, const int smemPerWarp, const int cCa
 // ---- host side ------------------------------------------------------------------------------------
 static int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+template <int R, bool FAST>
+static int occupancy_one(int smemPerWarp, const DeviceInfo& dev, int* wpcOut, int* occOut) {
+    int wpc = PDA_MURTY_WPC;
+    while (wpc > 1 && wpc * smemPerWarp > dev.maxSmemOptin) wpc >>= 1;
+    const size_t smem = (size_t)wpc * smemPerWarp;
+    int occ = 0;
+    cudaError_t e = cudaFuncSetAttribute(murty_kernel<R, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, murty_kernel<R, FAST>, 32 * wpc, smem);
+    if (e != cudaSuccess) return cuda_fail(e, "occupancy query for murty_kernel");
+    *wpcOut = wpc;
+    *occOut = occ < 1 ? 1 : occ;
+    return PDA_OK;
+}
+template <int R>
+static int occupancy_r(MurtyGeometry* g, const DeviceInfo& dev) {
+    int rc = occupancy_one<R, false>(g->smemPerWarp, dev, &g->warpsPerCta, &g->ctasPerSm);
+    if (rc) return rc;
+    g->fastWarpsPerCta = g->warpsPerCta;
+    g->fastCtasPerSm = g->ctasPerSm;
+    if (g->fastOk) rc = occupancy_one<R, true>(g->fastSmemPerWarp, dev, &g->fastWarpsPerCta, &g->fastCtasPerSm);
+    return rc;
+}
+
 int murty_geometry(int32_t k, int32_t maxNumRow, int32_t maxNumCol, bool weights, const DeviceInfo& dev,
                    MurtyGeometry* g) {
     if (k < 1 || maxNumRow < 1 || maxNumCol < 1 || maxNumCol > maxNumRow)
@@ -339,59 +442,75 @@ int murty_geometry(int32_t k, int32_t maxNumRow, int32_t maxNumCol, bool weights
     g->heapTopOff = baseSmem;
     g->heapTopCap = topCap;
     g->smemPerWarp = baseSmem + topCap * (int)sizeof(HeapEntry);
+    // the pruning fast path (murty_kernel<R, true>): its open list never holds more than k + slack entries, so it lives
+    // in shared memory when that fits the same per-warp budget, else in the arena's heap region (group minima stay in
+    // shared memory either way).  Not offered for k <= 2 (nothing to prune) or lists beyond 64 groups.
+    g->pqCap = round_up(k + 2 * maxNumCol + PQ_SLACK + 32, 32);
+    g->fastOk = (k > 2 && g->pqCap <= 64 * 32 && (int64_t)g->pqCap * 12 <= g->heapBytes) ? 1 : 0;
+    const int fastBudget = (227 * 1024 - PDA_FAST_MINB * 1024) / (PDA_MURTY_WPC * PDA_FAST_MINB);
+    g->pqInSmem = (baseSmem + g->pqCap * 12 + (g->pqCap >> 5) * 8 <= fastBudget) ? 1 : 0;
+    g->fastSmemPerWarp = round_up(baseSmem + (g->pqCap >> 5) * 8 + (g->pqInSmem ? g->pqCap * 12 : 0), 16);
     if (g->smemPerWarp > dev.maxSmemOptin)
         return fail(PDA_ERR_UNSUPPORTED, "murty: a %d x %d problem needs %d B of shared memory per warp (limit %d)",
                     maxNumRow, maxNumCol, g->smemPerWarp, dev.maxSmemOptin);
-    int wpc = PDA_MURTY_WPC;
-    while (wpc > 1 && wpc * g->smemPerWarp > dev.maxSmemOptin) wpc >>= 1;
-    g->warpsPerCta = wpc;
-    // resident CTAs per SM, as the occupancy calculator sees this instantiation (registers, shared memory)
-    int occ = 0;
-    const int threads = 32 * wpc;
-    const size_t smem = (size_t)wpc * g->smemPerWarp;
-    cudaError_t e = cudaSuccess;
+    if (g->fastSmemPerWarp > dev.maxSmemOptin) g->fastOk = 0;
+    // resident CTAs per SM, as the occupancy calculator sees each instantiation (registers, shared memory)
+    int rc = PDA_OK;
     switch (g->R) {
-        case 1:
-            e = cudaFuncSetAttribute(murty_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, murty_kernel<1>, threads, smem);
-            break;
-        case 2:
-            e = cudaFuncSetAttribute(murty_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, murty_kernel<2>, threads, smem);
-            break;
-        default:
-            e = cudaFuncSetAttribute(murty_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, murty_kernel<4>, threads, smem);
-            break;
+        case 1: rc = occupancy_r<1>(g, dev); break;
+        case 2: rc = occupancy_r<2>(g, dev); break;
+        default: rc = occupancy_r<4>(g, dev); break;
     }
-    if (e != cudaSuccess) return cuda_fail(e, "occupancy query for murty_kernel");
-    g->ctasPerSm = occ < 1 ? 1 : occ;
-    return PDA_OK;
+    return rc;
 }
 
-template <int R>
+template <int R, bool FAST>
 static int launch_murty_r(const MurtyArgs& a, cudaStream_t stream) {
-    const int threads = 32 * a.geo.warpsPerCta;
-    const int smem = a.geo.warpsPerCta * a.geo.smemPerWarp;
-    PDA_CUDA_TRY(cudaFuncSetAttribute(murty_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int ctas = (a.nWarps + a.geo.warpsPerCta - 1) / a.geo.warpsPerCta;
-    murty_kernel<R><<<ctas, threads, smem, stream>>>(a);
+    const int wpc = FAST ? a.geo.fastWarpsPerCta : a.geo.warpsPerCta;
+    const int threads = 32 * wpc;
+    const int smem = wpc * (FAST ? a.geo.fastSmemPerWarp : a.geo.smemPerWarp);
+    PDA_CUDA_TRY(cudaFuncSetAttribute(murty_kernel<R, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int ctas = (a.nWarps + wpc - 1) / wpc;
+    murty_kernel<R, FAST><<<ctas, threads, smem, stream>>>(a);
     PDA_CUDA_TRY(cudaGetLastError());
     return PDA_OK;
 }
 
+template <bool FAST>
+static int launch_murty_any(const MurtyArgs& a, cudaStream_t stream) {
+    switch (a.geo.R) {
+        case 1: return launch_murty_r<1, FAST>(a, stream);
+        case 2: return launch_murty_r<2, FAST>(a, stream);
+        case 4: return launch_murty_r<4, FAST>(a, stream);
+    }
+    return fail(PDA_ERR_UNSUPPORTED, "murty: unsupported row-slot count %d", a.geo.R);
+}
+
+#ifdef PDA_FAST_STATS
+extern "C" void pda_debug_fast_stats(unsigned long long* out, int reset) {
+    cudaMemcpyFromSymbol(out, g_fastStats, sizeof(unsigned long long) * 8);
+    cudaMemcpyFromSymbol(out + 8, g_augStats, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_fastStats, z, sizeof(z)); cudaMemcpyToSymbol(g_augStats, z, sizeof(z)); }
+}
+#endif
+
 int launch_murty(const MurtyArgs& a, cudaStream_t stream) {
-    PDA_CUDA_TRY(cudaMemsetAsync(a.cursor, 0, sizeof(unsigned long long), stream));
+    // header of the workspace: cursor (8 B) | fallback count (4 B, +4 pad) | cursor of the fallback pass (8 B)
+    PDA_CUDA_TRY(cudaMemsetAsync(a.cursor, 0, 32, stream));
     if (a.order) {
         order_by_cost_kernel<<<1, 1024, 0, stream>>>(a.numCol, a.nProblems, a.order);
         PDA_CUDA_TRY(cudaGetLastError());
     }
-    switch (a.geo.R) {
-        case 1: return launch_murty_r<1>(a, stream);
-        case 2: return launch_murty_r<2>(a, stream);
-        case 4: return launch_murty_r<4>(a, stream);
-    }
-    return fail(PDA_ERR_UNSUPPORTED, "murty: unsupported row-slot count %d", a.geo.R);
+    if (!a.useFast) return launch_murty_any<false>(a, stream);
+    int rc = launch_murty_any<true>(a, stream);
+    if (rc) return rc;
+    // the exact kernel over whatever the fast one could not decide (usually nothing: it then finds a count of zero)
+    MurtyArgs b = a;
+    b.useFast = 0;
+    b.cursor = a.cursor2;
+    b.order = a.fallbackList;
+    b.nProblemsDev = a.fallbackCount;
+    return launch_murty_any<false>(b, stream);
 }
 
 template <int R>

@@ -125,7 +125,9 @@ static void* mapped_alias(const void* p, int device) {
 static int64_t order_bytes(int64_t nProblems) { return (nProblems + 63) / 64 * 256; }
 
 static int64_t murty_full_warps(const MurtyGeometry& g, const DeviceInfo& dev) {
-    return (int64_t)dev.smCount * g.ctasPerSm * g.warpsPerCta;
+    const int64_t exact = (int64_t)dev.smCount * g.ctasPerSm * g.warpsPerCta;
+    const int64_t fast = g.fastOk ? (int64_t)dev.smCount * g.fastCtasPerSm * g.fastWarpsPerCta : 0;
+    return std::max(exact, fast);  // one arena per warp of whichever kernel keeps more of them resident
 }
 
 // Which kernel a batch goes to.  One CTA per problem (murty_cta_kernel.cu) is the latency path: it wins while the batch
@@ -133,7 +135,7 @@ static int64_t murty_full_warps(const MurtyGeometry& g, const DeviceInfo& dev) {
 static std::atomic<int> g_murtyPath{PDA_MURTY_PATH_AUTO};
 static bool cta_eligible(int64_t nProblems, int32_t maxNumCol, const DeviceInfo& dev) {
     const int path = g_murtyPath.load();
-    if (path == PDA_MURTY_PATH_WARP || maxNumCol > PDA_CTA_MAX_COL) return false;
+    if (path == PDA_MURTY_PATH_WARP || path == PDA_MURTY_PATH_FAST || maxNumCol > PDA_CTA_MAX_COL) return false;
     return path == PDA_MURTY_PATH_CTA || nProblems <= 4LL * dev.smCount;
 }
 
@@ -145,7 +147,7 @@ int64_t pda_murty_workspace_bytes(int64_t nProblems, int32_t k, int32_t maxNumRo
     rc = murty_geometry(k, maxNumRow, maxNumCol, false, dev, &g);
     if (rc) return rc;
     int64_t warps = std::min<int64_t>(std::max<int64_t>(nProblems, 1), murty_full_warps(g, dev));
-    int64_t bytes = 256 + warps * g.arenaStride + order_bytes(nProblems);
+    int64_t bytes = 256 + warps * g.arenaStride + 2 * order_bytes(nProblems);  // cost order + fallback list
     if (cta_eligible(nProblems, maxNumCol, dev)) {
         CtaGeometry cg;
         if (murty_cta_geometry(k, maxNumRow, maxNumCol, false, dev, &g, &cg) == PDA_OK) {
@@ -157,7 +159,7 @@ int64_t pda_murty_workspace_bytes(int64_t nProblems, int32_t k, int32_t maxNumRo
 }
 
 int pda_murty_set_path(int32_t path) {
-    if (path < PDA_MURTY_PATH_AUTO || path > PDA_MURTY_PATH_CTA) return fail(PDA_ERR_INVALID, "murty: bad path %d", path);
+    if (path < PDA_MURTY_PATH_AUTO || path > PDA_MURTY_PATH_FAST) return fail(PDA_ERR_INVALID, "murty: bad path %d", path);
     return g_murtyPath.exchange(path);
 }
 
@@ -189,6 +191,9 @@ int pda_murty_batch(const double* costs, const int64_t* costOff, const int32_t* 
     a.cursor = reinterpret_cast<unsigned long long*>(workspace);
     a.arena = reinterpret_cast<unsigned char*>(workspace) + 256;
     a.order = nullptr;
+    a.fallbackCount = reinterpret_cast<unsigned*>(workspace) + 2;
+    a.cursor2 = reinterpret_cast<unsigned long long*>(workspace) + 2;
+    a.fallbackList = nullptr; a.nProblemsDev = nullptr; a.useFast = 0;
     if (cta_eligible(nProblems, maxNumCol, dev)) {
         const bool forced = g_murtyPath.load() == PDA_MURTY_PATH_CTA;
         CtaGeometry cg;
@@ -211,6 +216,14 @@ int pda_murty_batch(const double* costs, const int64_t* costOff, const int32_t* 
                                (long long)workspaceBytes, (long long)a.geo.arenaStride);
     a.nWarps = (int32_t)warps;
     a.order = ordered ? reinterpret_cast<int32_t*>(a.arena + warps * a.geo.arenaStride) : nullptr;
+    // The pruning kernel first, the exact kernel behind it for the problems with exact gain ties -- when the geometry
+    // admits it, the fallback list fits behind the arenas and the caller has not pinned the exact kernel.
+    const int64_t used = 256 + warps * a.geo.arenaStride + (ordered ? order_bytes(nProblems) : 0);
+    const int path = g_murtyPath.load();
+    if (a.geo.fastOk && path != PDA_MURTY_PATH_WARP && nProblems < (1LL << 31) && workspaceBytes >= used + order_bytes(nProblems)) {
+        a.useFast = 1;
+        a.fallbackList = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(workspace) + used);
+    }  // else (k <= 2, a list too long for shared-memory group minima, a tight workspace): the exact kernel alone
     return launch_murty(a, reinterpret_cast<cudaStream_t>(stream));
 }
 

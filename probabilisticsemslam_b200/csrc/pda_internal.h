@@ -40,6 +40,13 @@ struct MurtyGeometry {
     int pCap;           // doubles reserved for the weight accumulators per warp
     int warpsPerCta;
     int ctasPerSm;
+    // pruning fast path (murty_kernel<R, true>)
+    int fastOk;           // geometry admits the fast path
+    int pqCap;            // slots of its open list (multiple of 32)
+    int pqInSmem;         // list in shared memory (else in the arena's heap region)
+    int fastSmemPerWarp;
+    int fastWarpsPerCta;
+    int fastCtasPerSm;
 };
 int murty_geometry(int32_t k, int32_t maxNumRow, int32_t maxNumCol, bool weights, const DeviceInfo& dev,
                    MurtyGeometry* g);
@@ -59,6 +66,12 @@ struct MurtyArgs {
     int32_t* order;              // optional: problem indices, most expensive first (NULL = index order)
     int32_t nWarps;              // arenas available == warps allowed to run
     MurtyGeometry geo;
+    // pruning fast path: problems it cannot decide (exact gain ties) are appended here and redone by the exact kernel
+    unsigned* fallbackCount;           // zeroed by launch_murty
+    int32_t* fallbackList;             // [nProblems]
+    const unsigned* nProblemsDev;      // when set, the kernel takes its problem count from here (the fallback pass)
+    unsigned long long* cursor2;       // work cursor of the fallback pass
+    int32_t useFast;
 };
 int launch_murty(const MurtyArgs& a, cudaStream_t stream);
 
@@ -99,7 +112,7 @@ int launch_to_probs(double* values, const int64_t* off, const int64_t* len, int6
 // ---- permanents (permanent_kernel.cu) ------------------------------------------------------------
 int launch_permanent_batch(const double* mats, const int64_t* matOff, const int32_t* rows, const int32_t* cols,
                            int64_t nMats, int32_t maxDim, double* out, int32_t* status, void* workspace,
-                           int64_t workspaceBytes, cudaStream_t stream);
+                           int64_t workspaceBytes, cudaStream_t stream, int32_t maxSmall = -1, int32_t minSmall = 0);
 int launch_permanent_range(const double* A, int32_t n, uint64_t begin, uint64_t end, double* partial,
                            void* workspace, int64_t workspaceBytes, cudaStream_t stream);
 

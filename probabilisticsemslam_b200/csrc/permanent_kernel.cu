@@ -73,7 +73,14 @@ struct PermArgs {
     int ctasPerMat;     // CTAs (blockIdx.x) that share a matrix
     int maxN;           // largest dimension in the batch (sizes the shared-memory slots)
     dd* partial;        // [nMats * ctasPerMat]
+    int dpBits;         // matrices whose SMALLER side is <= dpBits go to perm_dp_kernel instead (-1: none)
 };
+
+// Matrices with a small side are not walked by the NW kernel at all: see perm_dp_kernel.
+constexpr int PERM_DP_MAX = 10;
+__device__ __forceinline__ bool perm_uses_dp(const int rows, const int cols, const int dpBits) {
+    return (rows < cols ? rows : cols) <= dpBits;
+}
 
 // Leading dimension of the matrix in shared memory.  When the threads of a warp flip DIFFERENT columns (the first
 // index of every aligned chunk) each lane reads column k at k*LD + j; with LD == NP the columns of a 24-row matrix
@@ -341,7 +348,7 @@ __global__ void __launch_bounds__(PERM_THREADS, perm_min_blocks(NP)) perm_kernel
     const bool live = m < a.nMats;
     const int rows = live ? a.rows[m] : 0, cols = live ? a.cols[m] : 0;
     const int n = rows > cols ? rows : cols;
-    const bool ok = live && n >= 1 && n <= NP && n <= PDA_MAX_PERM_DIM && n <= a.maxN;
+    const bool ok = live && n >= 1 && n <= NP && n <= PDA_MAX_PERM_DIM && n <= a.maxN && !perm_uses_dp(rows, cols, a.dpBits);
     if (ok) {
         const double* A = a.mats + a.matOff[m];
         // stage the matrix: ones outside the given block (nwPerm.cpp:226-228), zero rows beyond n
@@ -401,13 +408,66 @@ __global__ void __launch_bounds__(PERM_THREADS, perm_min_blocks(NP)) perm_kernel
     }
 }
 
+// ---- matrices with a small side: subset dynamic programme ---------------------------------------------------------
+// permanentExact pads an m x n matrix (m < n) with ones to n x n and divides by (n-m)! (nwPerm.cpp:223-230); what that
+// computes is the sum over all injective maps of the m short-side indices into the n long-side ones.  The NW walk
+// over the padded matrix costs n * 2^(n-1) and -- alternating signs over products of row sums -- cancels: on the
+// shapes permanentProb produces (3-8 detections against 10-30 landmark rows, entries spanning many decades) the
+// reference's own result is good to 1e-8 at best.  The same sum by dynamic programming over subsets of the SHORT side,
+// one long-side index at a time,
+//     f_j[S] = f_{j-1}[S] + sum_{i in S} B[i, j] * f_{j-1}[S \ {i}],        perm = f_n[all],
+// costs n * 2^m * m / 2 multiply-adds and, for the non-negative matrices of this path, adds only non-negative terms:
+// no cancellation, relative error ~ (n + m) ulp.  One warp per matrix, f double-buffered in shared memory, states
+// strided over the lanes (S ^ (1 << i) keeps the bank of S: conflict-free).  Used whenever the short side is at most
+// PERM_DP_MAX (square matrices included); the reference's n > 32 limit is kept (status 1) so callers see the same
+// "throws" behaviour.
+__device__ __forceinline__ void perm_dp_warp(const PermArgs& a, const int64_t it, const int rows, const int cols,
+                                             double* __restrict__ buf, double* __restrict__ out,
+                                             int32_t* __restrict__ status, const int lane) {
+    const int m = rows < cols ? rows : cols, n = rows < cols ? cols : rows;
+    if (n > PDA_MAX_PERM_DIM) { if (lane == 0) { out[it] = 0.0; if (status) status[it] = 1; } return; }  // nwPerm.cpp:327-330
+    const int cap = 1 << a.dpBits, states = 1 << m;
+    double* cur = buf;
+    double* nxt = cur + cap;
+    double* sb = cur + 2 * cap;
+    for (int S = lane; S < states; S += 32) cur[S] = (S == 0) ? 1.0 : 0.0;
+    const double* A = a.mats + a.matOff[it];
+    const bool shortRows = rows <= cols;
+    for (int j = 0; j < n; ++j) {
+        __syncwarp();
+        if (lane < m) sb[lane] = shortRows ? A[lane + (size_t)j * rows] : A[j + (size_t)lane * rows];
+        __syncwarp();
+        for (int S = lane; S < states; S += 32) {
+            double acc = cur[S];
+            unsigned bits = (unsigned)S;
+            while (bits) {
+                const int i = __ffs(bits) - 1;
+                bits &= bits - 1u;
+                acc = fma(sb[i], cur[S ^ (1 << i)], acc);
+            }
+            nxt[S] = acc;
+        }
+        double* t = cur; cur = nxt; nxt = t;
+    }
+    __syncwarp();
+    if (lane == 0) { out[it] = cur[states - 1]; if (status) status[it] = 0; }
+}
+
 // One warp per matrix: sums the per-CTA partials (lane-strided, then a fixed shuffle tree -- the order depends
 // only on ctasPerMat, so results are reproducible) and applies sign, factor 2 and the rectangular scale.
 __global__ void perm_finalize_kernel(const PermArgs a, double* __restrict__ out, int32_t* __restrict__ status,
                                      double* __restrict__ rangePartial) {
+    extern __shared__ __align__(16) double smemD[];
     const int lane = threadIdx.x & 31;
     const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (m >= a.nMats) return;
+    if (a.dpBits >= 0 && !a.rangeMode) {
+        const int rows = a.rows[m], cols = a.cols[m];
+        if (perm_uses_dp(rows, cols, a.dpBits)) {  // the NW kernel skipped this one
+            perm_dp_warp(a, m, rows, cols, smemD + (size_t)(threadIdx.x >> 5) * (2 * ((size_t)1 << a.dpBits) + 16), out, status, lane);
+            return;
+        }
+    }
     dd t;
     t.hi = 0.0;
     t.lo = 0.0;
@@ -493,17 +553,29 @@ static PermShape perm_shape(int64_t nMats, int maxDim, int smCount, unsigned lon
 
 int launch_permanent_batch(const double* mats, const int64_t* matOff, const int32_t* rows, const int32_t* cols,
                            int64_t nMats, int32_t maxDim, double* out, int32_t* status, void* workspace,
-                           int64_t workspaceBytes, cudaStream_t stream) {
+                           int64_t workspaceBytes, cudaStream_t stream, int32_t maxSmall, int32_t minSmall) {
     DeviceInfo dev;
     PDA_TRY(current_device_info(&dev));
     const int effDim = std::max(1, std::min<int>(maxDim, PDA_MAX_PERM_DIM));
+    // maxSmall / minSmall: bounds on min(rows, cols) over the batch when the caller knows them (else maxDim / 0)
+    const int dpBits = std::min(PERM_DP_MAX, std::max(0, std::min<int>(maxSmall < 0 ? maxDim : maxSmall, maxDim)));
+    const bool allDp = (maxSmall >= 0 ? maxSmall : maxDim) <= dpBits;   // nothing for the NW walk
+    const bool noneDp = minSmall > dpBits;
+    const size_t dpSmem = noneDp ? 0 : (size_t)4 * (2 * ((size_t)1 << dpBits) + 16) * sizeof(double);  // 4 warps per finalize CTA
+    if (dpSmem > 48 * 1024) PDA_CUDA_TRY(cudaFuncSetAttribute(perm_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dpSmem));
+    if (allDp) {
+        PermArgs d = {mats, matOff, rows, cols, nMats, 0, 0, 0, 1, 32, 0, effDim, nullptr, dpBits};
+        perm_finalize_kernel<<<(unsigned)((nMats + 3) / 4), 128, dpSmem, stream>>>(d, out, status, nullptr);
+        PDA_CUDA_TRY(cudaGetLastError());
+        return PDA_OK;
+    }
     PermShape sh = perm_shape(nMats, effDim, dev.smCount, 0);
     while (sh.ctasPerMat > 1 && (int64_t)sh.ctasPerMat * nMats * (int64_t)sizeof(dd) > workspaceBytes) sh.ctasPerMat >>= 1;
     if ((int64_t)sh.ctasPerMat * nMats * (int64_t)sizeof(dd) > workspaceBytes)
         return fail(PDA_ERR_WORKSPACE, "permanent: workspace of %lld B too small (need %lld)", (long long)workspaceBytes,
                     (long long)(nMats * (int64_t)sizeof(dd)));
     PermArgs a = {mats, matOff, rows, cols, nMats, 0, 0, 0, sh.chunk, sh.threadsPerMat, sh.ctasPerMat, effDim,
-                  reinterpret_cast<dd*>(workspace)};
+                  reinterpret_cast<dd*>(workspace), noneDp ? -1 : dpBits};
     // blockIdx.y is limited to 65535: slice the batch
     const int64_t slots = PERM_THREADS / sh.threadsPerMat, perLaunch = 65535 * slots;
     for (int64_t m0 = 0; m0 < nMats; m0 += perLaunch) {
@@ -513,7 +585,7 @@ int launch_permanent_batch(const double* mats, const int64_t* matOff, const int3
         s.partial = a.partial + m0 * sh.ctasPerMat;
         PDA_TRY(dispatch(s, stream));
     }
-    perm_finalize_kernel<<<(unsigned)((nMats + 3) / 4), 128, 0, stream>>>(a, out, status, nullptr);
+    perm_finalize_kernel<<<(unsigned)((nMats + 3) / 4), 128, dpSmem, stream>>>(a, out, status, nullptr);
     PDA_CUDA_TRY(cudaGetLastError());
     return PDA_OK;
 }
@@ -537,7 +609,7 @@ int launch_permanent_range(const double* A, int32_t n, uint64_t begin, uint64_t 
     struct { int64_t off; int32_t r, c; } desc = {0, n, n};
     PDA_CUDA_TRY(cudaMemcpyAsync(ws, &desc, 16, cudaMemcpyHostToDevice, stream));
     PermArgs a = {A, dOff, dRows, dCols, 1, begin, end, 1, sh.chunk, sh.threadsPerMat, sh.ctasPerMat, n,
-                  reinterpret_cast<dd*>(ws + 64)};
+                  reinterpret_cast<dd*>(ws + 64), -1};
     PDA_TRY(dispatch(a, stream));
     perm_finalize_kernel<<<1, 32, 0, stream>>>(a, nullptr, nullptr, partial);
     PDA_CUDA_TRY(cudaGetLastError());
@@ -592,9 +664,14 @@ int pda_permanent_batch_host(const double* mats, const int64_t* matOff, const in
     PDA_TRY(h2d(st.at<int64_t>(oOff), matOff, n, s));
     PDA_TRY(h2d(st.at<int32_t>(oR), rows, n, s));
     PDA_TRY(h2d(st.at<int32_t>(oC), cols, n, s));
+    int maxSmall = 0, minSmall = PDA_MAX_DIM;
+    for (int64_t i = 0; i < nMats; ++i) {
+        const int sm = std::min(rows[i], cols[i]);
+        maxSmall = std::max(maxSmall, sm); minSmall = std::min(minSmall, sm);
+    }
     PDA_TRY(launch_permanent_batch(st.at<double>(oM), st.at<int64_t>(oOff), st.at<int32_t>(oR), st.at<int32_t>(oC), nMats,
                                    maxDim, st.at<double>(oOut), st.at<int32_t>(oSt), st.at<unsigned char>(oWs),
-                                   (int64_t)wsBytes, s));
+                                   (int64_t)wsBytes, s, maxSmall, minSmall));
     PDA_TRY(d2h(out, st.at<double>(oOut), n, s));
     PDA_TRY(d2h(status, st.at<int32_t>(oSt), n, s));
     PDA_CUDA_TRY(cudaStreamSynchronize(s));

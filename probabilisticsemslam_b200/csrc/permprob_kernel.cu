@@ -228,7 +228,7 @@ struct ItemBuffers {
     double* perm; int32_t* permStatus; int32_t* negList; int32_t* negCount; void* ws; int64_t wsBytes;
 };
 
-int run_items(BuildArgs b, const ItemBuffers& ib, int64_t nItems, int maxDim, int permOpt, cudaStream_t s) {
+int run_items(BuildArgs b, const ItemBuffers& ib, int64_t nItems, int maxDim, int permOpt, cudaStream_t s, int maxSmall) {
     b.subset = nullptr; b.nWork = nItems; b.transpose = 1;
     b.mats = ib.mats; b.outRows = ib.rows; b.outCols = ib.cols; b.scale = ib.scale; b.itemStatus = ib.status;
     build_items_kernel<<<(unsigned)((nItems + BUILD_WARPS - 1) / BUILD_WARPS), 32 * BUILD_WARPS, 0, s>>>(b);
@@ -238,7 +238,7 @@ int run_items(BuildArgs b, const ItemBuffers& ib, int64_t nItems, int maxDim, in
                                               ib.permStatus, s));
     else
         PDA_TRY(launch_permanent_batch(ib.mats, ib.matOff, ib.rows, ib.cols, nItems, maxDim, ib.perm, ib.permStatus, ib.ws,
-                                       ib.wsBytes, s));
+                                       ib.wsBytes, s, maxSmall));
     PDA_CUDA_TRY(cudaMemsetAsync(ib.negCount, 0, 4, s));
     unscale_kernel<<<(unsigned)((nItems + 255) / 256), 256, 0, s>>>(ib.perm, ib.scale, nullptr, nItems, ib.negList, ib.negCount);
     PDA_CUDA_TRY(cudaGetLastError());
@@ -258,7 +258,7 @@ int run_items(BuildArgs b, const ItemBuffers& ib, int64_t nItems, int maxDim, in
         for (int32_t i = 0; i < nNeg; ++i) {
             const int64_t it = neg[(size_t)i];
             PDA_TRY(launch_permanent_batch(ib.mats, ib.matOff + it, ib.rows + it, ib.cols + it, 1, maxDim, ib.perm + it,
-                                           ib.permStatus + it, ib.ws, ib.wsBytes, s));
+                                           ib.permStatus + it, ib.ws, ib.wsBytes, s, maxSmall));
         }
         unscale_kernel<<<(unsigned)((nNeg + 255) / 256), 256, 0, s>>>(ib.perm, ib.scale, ib.negList, nNeg, nullptr, nullptr);
         PDA_CUDA_TRY(cudaGetLastError());
@@ -334,7 +334,9 @@ int pda_conditioned_permanent_batch_host(const double* mats, const int64_t* matO
     PDA_TRY(h2d(ib.matOff, slotOff.data(), n, s));
     BuildArgs b = {};
     b.mode = 1; b.P = st.at<double>(oA); b.pOff = st.at<int64_t>(oOff); b.rows = st.at<int32_t>(oR); b.cols = st.at<int32_t>(oC);
-    PDA_TRY(run_items(b, ib, nMats, maxDim, permOpt, s));
+    int maxSmall = 0;
+    for (int64_t i = 0; i < nMats; ++i) maxSmall = std::max(maxSmall, std::min(rows[i], cols[i]));
+    PDA_TRY(run_items(b, ib, nMats, maxDim, permOpt, s, maxSmall));
     PDA_TRY(d2h(out, ib.perm, n, s));
     PDA_TRY(d2h(status, ib.status, n, s));
     PDA_CUDA_TRY(cudaStreamSynchronize(s));
@@ -356,7 +358,7 @@ int pda_permanent_prob_batch_host(const double* costs, const int64_t* costOff, c
     while (p0 < nProblems) {
         int64_t p1 = p0, items = 0;
         size_t nCost = 0, nProb = 0;
-        int maxDim = 1;
+        int maxDim = 1, maxSmall = 0;
         size_t c0 = (size_t)costOff[p0];
         std::vector<int64_t> itemOff, locCostOff, locProbOff;
         std::vector<int32_t> itemProblem;
@@ -376,6 +378,7 @@ int pda_permanent_prob_batch_host(const double* costs, const int64_t* costOff, c
             nCost = std::max(nCost, (size_t)costOff[p1] - c0 + (size_t)((L + M) * M));
             nProb = std::max(nProb, (size_t)probOff[p1] - pr0 + (size_t)(M * (L + 1)));
             if (M > 1) maxDim = std::max<int>(maxDim, (int)std::min<int64_t>(PDA_MAX_PERM_DIM, std::max(L + M - 1, M - 1)));
+            if (M > 1) maxSmall = std::max<int>(maxSmall, (int)std::min<int64_t>(M - 1, L + M - 1));
             ++p1;
         }
         const size_t n = (size_t)(p1 - p0), nIt = (size_t)std::max<int64_t>(items, 1);
@@ -415,7 +418,7 @@ int pda_permanent_prob_batch_host(const double* costs, const int64_t* costOff, c
                 BuildArgs b = {};
                 b.mode = 0; b.P = st.at<double>(oP); b.pOff = st.at<int64_t>(oOff); b.nL = st.at<int32_t>(oL); b.nM = st.at<int32_t>(oM);
                 b.itemOff = st.at<int64_t>(oItemOff); b.itemProblem = st.at<int32_t>(oItemProb);
-                PDA_TRY(run_items(b, ib, items, maxDim, permOpt, s));
+                PDA_TRY(run_items(b, ib, items, maxDim, permOpt, s, maxSmall));
             }
             finish_probs_kernel<<<(unsigned)((n + BUILD_WARPS - 1) / BUILD_WARPS), 32 * BUILD_WARPS, 0, s>>>(
                 st.at<double>(oP), st.at<int64_t>(oOff), st.at<int32_t>(oL), st.at<int32_t>(oM), st.at<int64_t>(oItemOff), ib.perm,

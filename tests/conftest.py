@@ -36,10 +36,11 @@ def gpu_api():
     return api
 
 
-@pytest.fixture(params=["warp", "cta"])
+@pytest.fixture(params=["warp", "cta", "fast"])
 def murty_path(request, gpu_api):
-    """Runs a test once per Murty kernel: one warp per problem (throughput) and one CTA per problem (latency).
-    Both must give the reference's bits; "cta" applies wherever numCol <= 16, the warp kernel takes the rest."""
+    """Runs a test once per Murty kernel: one warp per problem with the exact heap ("warp"), one CTA per problem
+    (latency, "cta": applies wherever numCol <= 16, the warp kernel takes the rest) and the pruning kernel with its
+    exact fallback for tied problems ("fast": the default for large batches).  All must give the reference's bits."""
     prev = gpu_api.set_murty_path(request.param)
     yield request.param
     gpu_api.set_murty_path(prev)
