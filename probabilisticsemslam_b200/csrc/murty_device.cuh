@@ -45,6 +45,49 @@ __device__ __forceinline__ double from_key(unsigned khi, unsigned klo) {
     return __hiloint2double((int)(khi ^ (m | 0x80000000u)), (int)(klo ^ m));
 }
 constexpr unsigned KEY_INF_HI = 0xFFF00000u;  // key of +inf is (0xFFF00000, 0)
+constexpr int HI_INF = 0x7ff00000;            // high word of +inf (and the NaN marker's 0x7ff80000 lies above it)
+
+// Warp arg-min of doubles that are almost always >= +0.0 (reduced costs: tiny negatives appear only through rounding).
+// For non-negative doubles -- +inf and the positive NaN marker included -- (high word as a signed int, low word as
+// unsigned) orders like the numbers, so the common case needs no key conversion: REDUX.MIN.S32 on the high words,
+// REDUX.MIN.U32 on the low words of the lanes that tie, REDUX.MIN on the row index of the lanes that tie again.  A
+// negative minimum shows up as mhi < 0 and takes the order-preserving keys instead.
+// Returns the high word of the minimum in mhiOut (>= HI_INF: nothing finite), its value in `val`, its lowest row in `row`.
+__device__ __forceinline__ void warp_argmin(const double x, const int myRow, int& mhiOut, double& val, int& row) {
+    const int hi = __double2hiint(x);
+    const unsigned lo = (unsigned)__double2loint(x);
+    const int mhi = __reduce_min_sync(FULL, hi);
+    if (mhi >= 0) {
+        const unsigned mlo = __reduce_min_sync(FULL, (hi == mhi) ? lo : 0xffffffffu);
+        const bool win = (hi == mhi) && (lo == mlo);
+        row = (int)__reduce_min_sync(FULL, win ? (unsigned)myRow : 0xffffu);
+        val = __hiloint2double(mhi, (int)mlo);
+        mhiOut = mhi;
+    } else {
+        unsigned khi, klo;
+        to_key(x, khi, klo);
+        const unsigned kmhi = __reduce_min_sync(FULL, khi);
+        const unsigned kmlo = __reduce_min_sync(FULL, (khi == kmhi) ? klo : 0xffffffffu);
+        const bool win = (khi == kmhi) && (klo == kmlo);
+        row = (int)__reduce_min_sync(FULL, win ? (unsigned)myRow : 0xffffu);
+        val = from_key(kmhi, kmlo);
+        mhiOut = -1;  // a negative number: finite
+    }
+}
+__device__ __forceinline__ double warp_min_val(const double x) {
+    const int hi = __double2hiint(x);
+    const unsigned lo = (unsigned)__double2loint(x);
+    const int mhi = __reduce_min_sync(FULL, hi);
+    if (mhi >= 0) {
+        const unsigned mlo = __reduce_min_sync(FULL, (hi == mhi) ? lo : 0xffffffffu);
+        return __hiloint2double(mhi, (int)mlo);
+    }
+    unsigned khi, klo;
+    to_key(x, khi, klo);
+    const unsigned kmhi = __reduce_min_sync(FULL, khi);
+    const unsigned kmlo = __reduce_min_sync(FULL, (khi == kmhi) ? klo : 0xffffffffu);
+    return from_key(kmhi, kmlo);
+}
 
 __device__ __forceinline__ double warp_min(double x) {
 #pragma unroll
@@ -128,8 +171,11 @@ __device__ unsigned long long g_augStats[8];  // argmins, ff tried, ff applied, 
 //              come after the row, which the reference never makes).
 // If the test passes every row of F is scanned at its current candidate (parked in sm.spc), predecessors stay as
 // they are, and the stopper is the next row to scan: (closest, delta) are returned so the caller skips its own
-// arg-min.  If it fails nothing is changed and the caller steps normally.  Returns 0 = not applied,
-// 1 = applied, 2 = applied and nothing finite is left (infeasible).
+// arg-min.  If it fails nothing is changed and the caller steps normally.  With fewer than two rows in F there is
+// nothing to batch, but the work done so far already identifies the next row to scan (the stopper itself, or the one row
+// of F), so the caller's arg-min is saved all the same.  Returns 0 = nothing known, 1 = (closest, delta) is the
+// stopper and everything before it is retired, 2 = the same and nothing finite is left (infeasible), 3 = (closest,
+// delta) is the plain arg-min, nothing retired.
 template <int R>
 __device__ __forceinline__ int fast_forward(const int numColReal, const WarpSmem& sm, const Node<R>& nd,
                                             const double (&vEff)[R], const double (&uRow)[R], double (&cand)[R],
@@ -140,15 +186,11 @@ __device__ __forceinline__ int fast_forward(const int numColReal, const WarpSmem
 #pragma unroll
     for (int s = 0; s < R; ++s)
         if (nd.c4r[s] < numColReal && cand[s] < sb) { sb = cand[s]; sbs = s; }
-    unsigned khi, klo;
-    to_key(sb, khi, klo);
-    const unsigned mhi = __reduce_min_sync(FULL, khi);
-    const unsigned mlo = __reduce_min_sync(FULL, (khi == mhi) ? klo : 0xffffffffu);
-    const bool win = (khi == mhi) && (klo == mlo);
-    const int rT = (int)__reduce_min_sync(FULL, win ? (unsigned)(lane + 32 * sbs) : 0xffffu);
-    const double kT = from_key(mhi, mlo);
+    int mhi, rT;
+    double kT;
+    warp_argmin(sb, lane + 32 * sbs, mhi, kT, rT);
     // F and what its hops would offer
-    unsigned inF = 0u;
+    unsigned inF = 0u, fMask[R];
     double wmin = CUDART_INF;
     int nF = 0;
 #pragma unroll
@@ -160,13 +202,28 @@ __device__ __forceinline__ int fast_forward(const int numColReal, const WarpSmem
             const double w = cand[s] - uRow[s];
             wmin = (w < wmin) ? w : wmin;
         }
-        nF += __popc(__ballot_sync(FULL, f));
+        fMask[s] = __ballot_sync(FULL, f);
+        nF += __popc(fMask[s]);
     }
-    if (nF < 2) return 0;
-    to_key(wmin, khi, klo);
-    const unsigned whi = __reduce_min_sync(FULL, khi);
-    const unsigned wlo = __reduce_min_sync(FULL, (khi == whi) ? klo : 0xffffffffu);
-    const double W = from_key(whi, wlo);
+    if (nF == 0) {  // no padding-paired row comes before the stopper: the stopper IS the arg-min
+        closest = rT;
+        delta = kT;
+        return (mhi >= HI_INF) ? 2 : 1;
+    }
+    if (nF == 1) {  // the one row of F is the arg-min; it is scanned the ordinary way
+        int slot = 0;
+#pragma unroll
+        for (int s = 1; s < R; ++s) if (fMask[s]) slot = s;
+        unsigned msk = fMask[0];
+        double cv = cand[0];
+#pragma unroll
+        for (int s = 1; s < R; ++s) if (slot == s) { msk = fMask[s]; cv = cand[s]; }
+        const int src = __ffs(msk) - 1;
+        closest = src + 32 * slot;
+        delta = __shfl_sync(FULL, cv, src);
+        return 3;
+    }
+    const double W = warp_min_val(wmin);
     bool beats = false;
 #pragma unroll
     for (int s = 0; s < R; ++s) beats = beats || ((W - vEff[s]) < cand[s]);
@@ -180,7 +237,7 @@ __device__ __forceinline__ int fast_forward(const int numColReal, const WarpSmem
     }
     closest = rT;
     delta = kT;
-    return (mhi >= KEY_INF_HI) ? 2 : 1;
+    return (mhi >= HI_INF) ? 2 : 1;
 }
 
 // One shortest augmenting path from `startCol` over the rows flagged in scanBits
@@ -249,14 +306,9 @@ __device__ __forceinline__ int augment_from(const int startCol, const int numCol
             int bs = 0;
 #pragma unroll
             for (int s = 1; s < R; ++s) if (cand[s] < best || best != best) { best = cand[s]; bs = s; }
-            unsigned khi, klo;
-            to_key(best, khi, klo);
-            const unsigned mhi = __reduce_min_sync(FULL, khi);
-            if (mhi >= KEY_INF_HI) return 1;  // minVal == +inf (:197, :327): nothing finite is left
-            const unsigned mlo = __reduce_min_sync(FULL, (khi == mhi) ? klo : 0xffffffffu);
-            const bool win = (khi == mhi) && (klo == mlo);
-            closest = (int)__reduce_min_sync(FULL, win ? (unsigned)(lane + 32 * bs) : 0xffffu);
-            delta = from_key(mhi, mlo);
+            int mhi;
+            warp_argmin(best, lane + 32 * bs, mhi, delta, closest);
+            if (mhi >= HI_INF) return 1;  // minVal == +inf (:197, :327): nothing finite is left
         }
         if (LIMIT && delta > limit) return 2;
         if (lane == 0) sm.spc[closest] = delta;
@@ -650,20 +702,33 @@ __device__ __forceinline__ double stage_safe_matrix(const double* Cg, double* Cs
     return d;
 }
 
+struct EmitPtrs { int64_t* c4r; int64_t* r4c; double* gain; };
+__device__ __forceinline__ EmitPtrs emit_ptrs(const MurtyArgs& a, const long long p) {
+    EmitPtrs e;
+    e.c4r = a.c4rBest ? a.c4rBest + a.c4rOff[p] : nullptr;
+    e.r4c = a.r4cBest ? a.r4cBest + a.r4cOff[p] : nullptr;
+    e.gain = a.gainBest ? a.gainBest + p * (long long)a.k : nullptr;
+    return e;
+}
 template <int R>
-__device__ __forceinline__ void emit(const MurtyArgs& a, const long long p, const int slot, const int n, const int nc,
-                                     const Node<R>& nd, const double gainOut, const int lane) {
-    if (a.c4rBest) {
-        int64_t* o = a.c4rBest + a.c4rOff[p] + (int64_t)slot * n;
+__device__ __forceinline__ void emit(const EmitPtrs& e, const int slot, const int n, const int nc, const Node<R>& nd,
+                                     const double gainOut, const int lane) {
+    if (e.c4r) {
+        int64_t* o = e.c4r + (int64_t)slot * n;
 #pragma unroll
         for (int s = 0; s < R; ++s) if (lane + 32 * s < n) o[lane + 32 * s] = (int64_t)nd.c4r[s];
     }
-    if (a.r4cBest) {
-        int64_t* o = a.r4cBest + a.r4cOff[p] + (int64_t)slot * nc;
+    if (e.r4c) {
+        int64_t* o = e.r4c + (int64_t)slot * nc;
 #pragma unroll
         for (int s = 0; s < R; ++s) if (lane + 32 * s < nc) o[lane + 32 * s] = (int64_t)nd.r4c[s];
     }
-    if (a.gainBest && lane == 0) a.gainBest[p * (long long)a.k + slot] = gainOut;
+    if (e.gain && lane == 0) e.gain[slot] = gainOut;
+}
+template <int R>
+__device__ __forceinline__ void emit(const MurtyArgs& a, const long long p, const int slot, const int n, const int nc,
+                                     const Node<R>& nd, const double gainOut, const int lane) {
+    emit<R>(emit_ptrs(a, p), slot, n, nc, nd, gainOut, lane);
 }
 
 // assignmentProb / bruteForceProb accumulation of one hypothesis (assignment.cpp:620-640, 916-937)

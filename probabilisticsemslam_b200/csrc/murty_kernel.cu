@@ -123,7 +123,8 @@ __device__ void solve_problem(const MurtyArgs& a, const long long p, const WarpS
         gain0Out = -gain + CDelta;
     }
     const bool cutting = a.cutMode != PDA_CUT_NONE;
-    emit<R>(a, p, 0, n, nc, nd, gain0Out, lane);
+    const EmitPtrs ep = emit_ptrs(a, p);  // per-problem output bases, fetched once
+    emit<R>(ep, 0, n, nc, nd, gain0Out, lane);
     double total = 0.0;
     if (wantW && nc > 1) add_weight<R>(a, sm, nd, nc, nL, gain0Out, gain0Out, total, lane);
 
@@ -238,7 +239,7 @@ __device__ void solve_problem(const MurtyArgs& a, const long long p, const WarpS
             gainOut = -gain + CDelta;
             if (a.cutMode == PDA_CUT_RELATIVE && gainOut < gain0Out - a.cutoff) stop = true;
         }
-        emit<R>(a, p, sweep, n, nc, nd, gainOut, lane);
+        emit<R>(ep, sweep, n, nc, nd, gainOut, lane);
         if (stop) break;
         if (wantW && nc > 1) add_weight<R>(a, sm, nd, nc, nL, gain0Out, gainOut, total, lane);
     }
@@ -256,16 +257,19 @@ __device__ void solve_problem(const MurtyArgs& a, const long long p, const WarpS
     }
 }
 
+// Per-warp shared memory: the mirrors first, at offsets that depend only on R (so every access is base + immediate and
+// one register carries them all), then the cost matrix and the weight accumulators.
+template <int R>
 __device__ __forceinline__ WarpSmem carve(unsigned char* base, const MurtyGeometry& g) {
     WarpSmem sm;
-    const int D = 32 * g.R;
-    sm.C = reinterpret_cast<double*>(base);
-    sm.u = sm.C + g.cCap;
+    constexpr int D = 32 * R;
+    sm.u = reinterpret_cast<double*>(base);
     sm.spc = sm.u + D;
-    sm.acc = sm.spc + D;
-    sm.r4c = reinterpret_cast<short*>(sm.acc + g.pCap);
+    sm.r4c = reinterpret_cast<short*>(base + 16 * D);
     sm.pred = sm.r4c + D;
-    sm.c4r = reinterpret_cast<unsigned short*>(sm.pred + D);
+    sm.c4r = reinterpret_cast<unsigned short*>(base + 20 * D);
+    sm.C = reinterpret_cast<double*>(base + 22 * D);  // 704 R bytes: a multiple of 16
+    sm.acc = sm.C + g.cCap;
     return sm;
 }
 
@@ -277,7 +281,7 @@ __global__ void __launch_bounds__(32 * PDA_MURTY_WPC, FAST ? PDA_FAST_MINB : PDA
     if (gw >= a.nWarps) return;
     const int smemPerWarp = FAST ? a.geo.fastSmemPerWarp : a.geo.smemPerWarp;
     unsigned char* mySmem = smemRaw + (size_t)warp * smemPerWarp;
-    const WarpSmem sm = carve(mySmem, a.geo);
+    const WarpSmem sm = carve<R>(mySmem, a.geo);
     unsigned char* arena = a.arena + (size_t)gw * a.geo.arenaStride;
     Heap heap;
     heap.deep = reinterpret_cast<HeapEntry*>(arena);
@@ -342,7 +346,7 @@ __global__ void lap_kernel(const LapArgs a, const int smemPerWarp, const int cCa
     if (p >= a.nProblems) return;
     MurtyGeometry g;
     g.R = R; g.cCap = cCap; g.pCap = 0;
-    const WarpSmem sm = carve(smemRaw + (size_t)warp * smemPerWarp, g);
+    const WarpSmem sm = carve<R>(smemRaw + (size_t)warp * smemPerWarp, g);
     const int n = a.numRow[p], nc = a.numCol[p];
     const int ncGain = a.numCol4Gain ? a.numCol4Gain[p] : nc;
     if (nc < 0 || nc > n || n > 32 * R) { if (lane == 0 && a.feasible) a.feasible[p] = 0; return; }
