@@ -85,5 +85,17 @@ inline double conditionedPermanent(const Eigen::MatrixXd& A, int permOpt) {
 std::vector<std::vector<std::vector<double> > > assignmentProbBatch(const std::vector<std::vector<double> >& costs,
                                                                     const std::vector<size_t>& nL,
                                                                     const std::vector<size_t>& nM, size_t k);
+/* the same batch spread over several GPUs of this process (one host thread per device, contiguous slices, no
+ * collective: pda_murty_batch_host_multi); `devices` lists CUDA device ordinals */
+std::vector<std::vector<std::vector<double> > > assignmentProbBatch(const std::vector<std::vector<double> >& costs,
+                                                                    const std::vector<size_t>& nL,
+                                                                    const std::vector<size_t>& nM, size_t k,
+                                                                    const std::vector<int>& devices);
+/* permanentProb (assignment.cpp:145-290) for many problems, optionally over several GPUs (empty `devices` = the shim's
+ * device).  Throws where the reference throws. */
+std::vector<std::vector<std::vector<double> > > permanentProbBatch(const std::vector<std::vector<double> >& costs,
+                                                                   const std::vector<size_t>& nL,
+                                                                   const std::vector<size_t>& nM, int permOpt,
+                                                                   const std::vector<int>& devices = std::vector<int>());
 
 #endif

@@ -31,6 +31,9 @@
 double permanentExactRaw(const double* A, size_t rows, size_t cols);
 long double permanentExactLongRaw(const double* A, size_t rows, size_t cols);
 double permanentApproximationRaw(const double* A, size_t rows, size_t cols, size_t iterations);
+/* ONE n x n matrix over several GPUs of this process: the Gray range of the NW walk (nwPerm.cpp:294-323) split across
+ * `nDevices` CUDA device ordinals, partial sums combined on the host in device order (pda_permanent_sharded_host) */
+double permanentExactShardedRaw(const double* A, size_t n, const int* devices, size_t nDevices);
 
 #ifdef PDA_HAVE_EIGEN
 inline double permanentExact(const Eigen::MatrixXd& A) { return permanentExactRaw(A.data(), size_t(A.rows()), size_t(A.cols())); }
@@ -38,6 +41,7 @@ inline double permanentExactSquare(const Eigen::MatrixXd& A) { return permanentE
 inline long double permanentExactLong(const Eigen::MatrixXd& A) { return permanentExactLongRaw(A.data(), size_t(A.rows()), size_t(A.cols())); }
 inline double permanentApproximation(const Eigen::MatrixXd& A, size_t iterations) { return permanentApproximationRaw(A.data(), size_t(A.rows()), size_t(A.cols()), iterations); }
 inline double permanentApproximationSquare(const Eigen::MatrixXd& A, size_t iterations) { return permanentApproximationRaw(A.data(), size_t(A.rows()), size_t(A.cols()), iterations); }
+inline double permanentExactSharded(const Eigen::MatrixXd& A, const int* devices, size_t nDevices) { return permanentExactShardedRaw(A.data(), size_t(A.rows()), devices, nDevices); }
 inline double permanentFastest(const Eigen::MatrixXd& A) {  /* nwPerm.cpp:19-33 */
     return (A.rows() > A.cols() ? A.rows() : A.cols()) <= 20 ? permanentExact(A) : permanentApproximation(A, 300);
 }

@@ -110,6 +110,20 @@ int pda_murty_batch_host(const double* costs, const int64_t* costOff, const int3
                          int32_t weightMode, double* probs, const int64_t* probOff, const int32_t* nL,
                          int32_t device);
 
+/* The same over SEVERAL devices of one process ("single process drives all GPUs"): the batch is cut into
+ * one contiguous slice per entry of `devices`, every slice runs pda_murty_batch_host on its own host thread and device
+ * (own lock, staging arena and streams), and the results land directly in the caller's arrays -- problems are
+ * independent, so there is no data-path collective.  Offsets stay absolute: pass the arrays of the whole batch.
+ * What a frames x probWin window batch of the SLAM loop (slidingWindow.cpp:260-339, system.cpp:268) would call. */
+int pda_murty_batch_host_multi(const double* costs, const int64_t* costOff, const int32_t* numRow, const int32_t* numCol,
+                               int64_t nProblems, int32_t k, int32_t cutMode, double cutoff, int32_t maximize,
+                               int32_t cutMaximize,
+                               int64_t* row4colBest, const int64_t* r4cOff,
+                               int64_t* col4rowBest, const int64_t* c4rOff,
+                               double* gainBest, int32_t* nFound,
+                               int32_t weightMode, double* probs, const int64_t* probOff, const int32_t* nL,
+                               const int32_t* devices, int32_t nDevices);
+
 /* Single LAP on a rectangular matrix without padding: assign2D (shortestPathCPP.hpp:144-149) when
  * makeSafe != 0, shortestPathCPP (hpp:178-182) on an already-safe matrix otherwise.
  * Per problem p: col4row[rowOff.. +numRow], row4col[colOff.. +numCol], u[colOff..], v[rowOff..],
@@ -225,6 +239,16 @@ int pda_permanent_range(const double* A, int32_t n, uint64_t begin, uint64_t end
 int pda_permanent_range_host(const double* A, int32_t n, uint64_t begin, uint64_t end, double* partial,
                              int32_t device);
 
+/* Multi-device forms.  pda_permanent_batch_host_multi: independent matrices, one contiguous slice per device, no
+ * collective.  pda_permanent_sharded_host: ONE matrix (BASELINE config 5, n = 28): the Gray index range [0, 2^(n-1)) of
+ * the NW walk (nwPerm.cpp:294-323) is cut into a power-of-two number of equal pieces, one per device (devices beyond the
+ * largest power of two <= nDevices stay idle), each device runs pda_permanent_range on its piece, and the 16-byte
+ * (hi, lo) partial sums are gathered by the host and added in device order with an error-free two-sum -- the one real
+ * exchange step of this path, and a deterministic one. */
+int pda_permanent_batch_host_multi(const double* mats, const int64_t* matOff, const int32_t* rows, const int32_t* cols,
+                                   int64_t nMats, double* out, int32_t* status, const int32_t* devices, int32_t nDevices);
+int pda_permanent_sharded_host(const double* A, int32_t n, const int32_t* devices, int32_t nDevices, double* out);
+
 /* Huber's randomised approximation of the permanent: permanentApproximation / permanentApproximationSquare with their
  * sinkhorn / hl_factor / pickRowFromProbs helpers (nwPerm.h:27-35, nwPerm.cpp:36-211), `iterations` acceptance /
  * rejection trials per matrix (the reference uses apprxIter = 300, assignment.cpp:10).  Rectangular input is padded with
@@ -252,6 +276,13 @@ int pda_conditioned_permanent_batch_host(const double* mats, const int64_t* matO
 int pda_permanent_prob_batch_host(const double* costs, const int64_t* costOff, const int32_t* nL,
                                   const int32_t* nM, int64_t nProblems, int32_t permOpt,
                                   double* probs, const int64_t* probOff, int32_t* status, int32_t device);
+
+/* The same over several devices: contiguous slices of problems, one per device (the (nL+1) * nM sub-permanents of a
+ * problem stay together; assignment.cpp:213-246). */
+int pda_permanent_prob_batch_host_multi(const double* costs, const int64_t* costOff, const int32_t* nL,
+                                        const int32_t* nM, int64_t nProblems, int32_t permOpt,
+                                        double* probs, const int64_t* probOff, int32_t* status,
+                                        const int32_t* devices, int32_t nDevices);
 
 #ifdef __cplusplus
 }

@@ -25,6 +25,8 @@ SIGNATURES = {
                                   ptr, ptr, ptr, ptr, ptr, ptr, i32, ptr, ptr, ptr, ptr, i64, ptr]),
     "pda_murty_batch_host": (C.c_int, [ptr, ptr, ptr, ptr, i64, i32, i32, dbl, i32, i32,
                                        ptr, ptr, ptr, ptr, ptr, ptr, i32, ptr, ptr, ptr, i32]),
+    "pda_murty_batch_host_multi": (C.c_int, [ptr, ptr, ptr, ptr, i64, i32, i32, dbl, i32, i32,
+                                             ptr, ptr, ptr, ptr, ptr, ptr, i32, ptr, ptr, ptr, ptr, i32]),
     "pda_lap_batch": (C.c_int, [ptr, ptr, ptr, ptr, ptr, i64, i32, i32, i32, i32, ptr, ptr,
                                 ptr, ptr, ptr, ptr, ptr, ptr, ptr, ptr]),
     "pda_lap_batch_host": (C.c_int, [ptr, ptr, ptr, ptr, ptr, i64, i32, i32, ptr, ptr,
@@ -47,11 +49,14 @@ SIGNATURES = {
     "pda_permanent_batch_host": (C.c_int, [ptr, ptr, ptr, ptr, i64, ptr, ptr, i32]),
     "pda_permanent_range": (C.c_int, [ptr, i32, u64, u64, ptr, ptr, i64, ptr]),
     "pda_permanent_range_host": (C.c_int, [ptr, i32, u64, u64, ptr, i32]),
+    "pda_permanent_batch_host_multi": (C.c_int, [ptr, ptr, ptr, ptr, i64, ptr, ptr, ptr, i32]),
+    "pda_permanent_sharded_host": (C.c_int, [ptr, i32, ptr, i32, ptr]),
     "pda_permanent_approx_batch": (C.c_int, [ptr, ptr, ptr, ptr, i64, i32, u64, ptr, ptr, ptr]),
     "pda_permanent_approx_batch_host": (C.c_int, [ptr, ptr, ptr, ptr, i64, i32, u64, ptr, ptr, i32]),
     "pda_set_approx_seed": (None, [u64]),
     "pda_conditioned_permanent_batch_host": (C.c_int, [ptr, ptr, ptr, ptr, i64, i32, ptr, ptr, i32]),
     "pda_permanent_prob_batch_host": (C.c_int, [ptr, ptr, ptr, ptr, i64, i32, ptr, ptr, ptr, i32]),
+    "pda_permanent_prob_batch_host_multi": (C.c_int, [ptr, ptr, ptr, ptr, i64, i32, ptr, ptr, ptr, ptr, i32]),
 }
 
 

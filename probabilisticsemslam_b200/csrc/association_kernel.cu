@@ -111,8 +111,8 @@ int pda_association_probs_batch_host(const double* costs, const int64_t* costOff
         nProb = std::max(nProb, (size_t)probOff[p] + (size_t)M * (L + 1));
         maxR = std::max(maxR, L + M); maxC = std::max(maxC, M);
     }
-    std::lock_guard<std::mutex> lk(g_hostMu);
-    PDA_TRY(check_device(device));
+    DeviceScope scope;
+    PDA_TRY(scope.enter(device));
     const int64_t wsBytes = pda_association_workspace_bytes(nProblems, (int64_t)nCost, (int64_t)nRows, (int64_t)nProb, k, maxR, maxC);
     if (wsBytes < 0) return (int)wsBytes;
     if (8 * (nCost + nProb + 3 * n) + 8 * n <= PDA_PACKED_LIMIT) {  // small call (the per-frame SLAM shape): one pinned copy each way

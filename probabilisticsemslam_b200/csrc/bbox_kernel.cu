@@ -104,8 +104,8 @@ extern "C" int pda_asgn_bb_batch_host(const double* boxesL, const int64_t* offL,
     const size_t n = numRow.size();
     if (n == 0) return PDA_OK;
     if (!boxesL || !boxesR) return fail(PDA_ERR_INVALID, "asgn_bb: NULL boxes");
-    std::lock_guard<std::mutex> lk(g_hostMu);
-    PDA_TRY(check_device(device));
+    DeviceScope scope;
+    PDA_TRY(scope.enter(device));
     const int64_t wsBytes = pda_murty_workspace_bytes((int64_t)n, 1, maxR, maxC);
     if (wsBytes < 0) return (int)wsBytes;
     Stage st(device);

@@ -17,8 +17,11 @@
 namespace pda {
 
 static thread_local char g_err[512] = "";
+static thread_local unsigned long long g_failures = 0;
+unsigned long long failure_count() { return g_failures; }
 
 int fail(int code, const char* fmt, ...) {
+    ++g_failures;
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
@@ -26,6 +29,7 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 int cuda_fail(cudaError_t e, const char* what) {
+    ++g_failures;
     snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
     (void)cudaGetLastError();
     return PDA_ERR_CUDA;
@@ -51,10 +55,7 @@ int current_device_info(DeviceInfo* out) {
 static std::atomic<uint64_t> g_approxSeed{20260217ULL};
 uint64_t approx_seed() { return g_approxSeed.load(); }
 
-std::mutex g_hostMu;
-std::vector<DevArena> g_arenas;
-std::vector<HostStreams> g_hostStreams;
-PinnedBuf g_pinned = {nullptr, 0};
+DeviceCtx g_dev[PDA_MAX_DEVICES];
 
 }  // namespace pda
 
@@ -240,22 +241,37 @@ int pda_murty_batch_host(const double* costs, const int64_t* costOff, const int3
     if (!costs || !costOff || !numRow || !numCol || !nFound) return fail(PDA_ERR_INVALID, "murty: NULL input");
     if (k < 1) return fail(PDA_ERR_INVALID, "murty: k < 1");
     if (weightMode && (!probs || !probOff || !nL)) return fail(PDA_ERR_INVALID, "murty: weights requested without probs/probOff/nL");
+    // Every array is addressed through per-problem offsets; only the range [lo, hi) this batch touches is staged (a
+    // shard of a larger batch -- pda_murty_batch_host_multi -- passes the whole arrays and its own slice of offsets).
     int maxR = 0, maxC = 0;
-    size_t nCost = 0, nR4c = 0, nC4r = 0, nProb = 0;
+    struct Range { size_t lo = ~(size_t)0, hi = 0; void add(size_t o, size_t n) { lo = std::min(lo, o); hi = std::max(hi, o + n); } size_t len() const { return hi > lo ? hi - lo : 0; } };
+    Range rCost, rR4c, rC4r, rProb;
+    bool contiguous = true;  // problem p+1 starts at or after the end of problem p in every array: chunks are ranges
     for (int64_t p = 0; p < nProblems; ++p) {
         const int r = numRow[p], c = numCol[p];
         if (r < 1 || c < 1 || c > r) return fail(PDA_ERR_INVALID, "murty: problem %lld is %d x %d (need numRow >= numCol >= 1)", (long long)p, r, c);
+        if (costOff[p] < 0 || (row4colBest && r4cOff[p] < 0) || (col4rowBest && c4rOff[p] < 0) || (weightMode && probOff[p] < 0))
+            return fail(PDA_ERR_INVALID, "murty: negative offset at problem %lld", (long long)p);
         maxR = std::max(maxR, r); maxC = std::max(maxC, c);
-        nCost = std::max(nCost, (size_t)costOff[p] + (size_t)r * c);
-        if (row4colBest) nR4c = std::max(nR4c, (size_t)r4cOff[p] + (size_t)k * c);
-        if (col4rowBest) nC4r = std::max(nC4r, (size_t)c4rOff[p] + (size_t)k * r);
+        if (p > 0) {
+            const int pr = numRow[p - 1], pc = numCol[p - 1];
+            if (costOff[p] < costOff[p - 1] + (int64_t)pr * pc) contiguous = false;
+            if (row4colBest && r4cOff[p] < r4cOff[p - 1] + (int64_t)k * pc) contiguous = false;
+            if (col4rowBest && c4rOff[p] < c4rOff[p - 1] + (int64_t)k * pr) contiguous = false;
+            if (weightMode && probOff[p] < probOff[p - 1] + (int64_t)pc * (nL[p - 1] + 1)) contiguous = false;
+        }
+        rCost.add((size_t)costOff[p], (size_t)r * c);
+        if (row4colBest) rR4c.add((size_t)r4cOff[p], (size_t)k * c);
+        if (col4rowBest) rC4r.add((size_t)c4rOff[p], (size_t)k * r);
         if (weightMode) {
             if (nL[p] + c != r) return fail(PDA_ERR_INVALID, "murty: problem %lld has nL + numCol != numRow", (long long)p);
-            nProb = std::max(nProb, (size_t)probOff[p] + (size_t)c * (nL[p] + 1));
+            rProb.add((size_t)probOff[p], (size_t)c * (nL[p] + 1));
         }
     }
-    std::lock_guard<std::mutex> lk(g_hostMu);
-    PDA_TRY(check_device(device));
+    const size_t nCost = rCost.len(), nR4c = rR4c.len(), nC4r = rC4r.len(), nProb = rProb.len();
+    const size_t loCost = rCost.lo, loR4c = nR4c ? rR4c.lo : 0, loC4r = nC4r ? rC4r.lo : 0, loProb = nProb ? rProb.lo : 0;
+    DeviceScope scope;
+    PDA_TRY(scope.enter(device));
     int64_t wsBytes = pda_murty_workspace_bytes(nProblems, k, maxR, maxC);
     if (wsBytes < 0) return (int)wsBytes;
     const size_t n = (size_t)nProblems;
@@ -263,23 +279,23 @@ int pda_murty_batch_host(const double* costs, const int64_t* costOff, const int3
     if (ioBytes <= PDA_PACKED_LIMIT) {  // small call: one pinned copy each way
         Stage st(device);
         PackedIO io(st);
-        const size_t oCost = io.in(costs, nCost * 8), oCostOff = io.in(costOff, n * 8), oNR = io.in(numRow, n * 4), oNC = io.in(numCol, n * 4);
+        const size_t oCost = io.in(costs + loCost, nCost * 8), oCostOff = io.in(costOff, n * 8), oNR = io.in(numRow, n * 4), oNC = io.in(numCol, n * 4);
         const size_t oR4cOff = io.in(row4colBest ? r4cOff : nullptr, n * 8), oC4rOff = io.in(col4rowBest ? c4rOff : nullptr, n * 8);
         const size_t oProbOff = io.in(weightMode ? probOff : nullptr, n * 8), oNL = io.in(weightMode ? nL : nullptr, n * 4);
         const size_t oFound = io.out(nFound, n * 4), oGain = io.out(gainBest, gainBest ? n * (size_t)k * 8 : 0);
-        const size_t oProb = io.out(weightMode ? probs : nullptr, nProb * 8);
-        const size_t oR4c = io.out(row4colBest, nR4c * 8), oC4r = io.out(col4rowBest, nC4r * 8);
+        const size_t oProb = io.out(weightMode ? probs + loProb : nullptr, nProb * 8);
+        const size_t oR4c = io.out(row4colBest ? row4colBest + loR4c : nullptr, nR4c * 8), oC4r = io.out(col4rowBest ? col4rowBest + loC4r : nullptr, nC4r * 8);
         const size_t oWs = st.reserve((size_t)wsBytes);
         PDA_TRY(st.commit());
         HostStreams* hs = nullptr;
         PDA_TRY(host_streams(device, &hs));
         PDA_TRY(io.upload(hs->run));
-        PDA_TRY(pda_murty_batch(st.at<double>(oCost), st.at<int64_t>(oCostOff), st.at<int32_t>(oNR), st.at<int32_t>(oNC), nProblems,
+        PDA_TRY(pda_murty_batch(st.at<double>(oCost) - loCost, st.at<int64_t>(oCostOff), st.at<int32_t>(oNR), st.at<int32_t>(oNC), nProblems,
                                 maxR, maxC, k, cutMode, cutoff, maximize, cutMaximize,
-                                row4colBest ? st.at<int64_t>(oR4c) : nullptr, st.at<int64_t>(oR4cOff),
-                                col4rowBest ? st.at<int64_t>(oC4r) : nullptr, st.at<int64_t>(oC4rOff),
+                                row4colBest ? st.at<int64_t>(oR4c) - loR4c : nullptr, st.at<int64_t>(oR4cOff),
+                                col4rowBest ? st.at<int64_t>(oC4r) - loC4r : nullptr, st.at<int64_t>(oC4rOff),
                                 gainBest ? st.at<double>(oGain) : nullptr, st.at<int32_t>(oFound),
-                                weightMode, weightMode ? st.at<double>(oProb) : nullptr, st.at<int64_t>(oProbOff),
+                                weightMode, weightMode ? st.at<double>(oProb) - loProb : nullptr, st.at<int64_t>(oProbOff),
                                 st.at<int32_t>(oNL), st.at<unsigned char>(oWs), wsBytes, hs->run));
         return io.download(hs->run);
     }
@@ -295,21 +311,19 @@ int pda_murty_batch_host(const double* costs, const int64_t* costOff, const int3
     const size_t oProb = st.reserve(probsDev ? 0 : nProb * 8), oProbOff = st.reserve(n * 8), oNL = st.reserve(n * 4);
     const size_t oWs = st.reserve((size_t)wsBytes);
     PDA_TRY(st.commit());
+    // device-side bases such that base + offset[p] lands inside the staged range
+    double* const dCost = costsDev ? costsDev : st.at<double>(oCost) - loCost;
+    int64_t* const dR4c = row4colBest ? st.at<int64_t>(oR4c) - loR4c : nullptr;
+    int64_t* const dC4r = col4rowBest ? st.at<int64_t>(oC4r) - loC4r : nullptr;
+    double* const dProb = weightMode ? (probsDev ? probsDev : st.at<double>(oProb) - loProb) : nullptr;
 
     // Large batches are cut into chunks that flow through three streams (copy in / run / copy out), so the PCIe
-    // transfers of one chunk overlap the kernel of another.  That needs every offset array to be non-decreasing
-    // (then a chunk's inputs and outputs are contiguous ranges); otherwise, and for small batches, one chunk.
-    bool monotonic = true;
-    for (size_t p = 1; p < n && monotonic; ++p) {
-        if (costOff[p] < costOff[p - 1]) monotonic = false;
-        if (row4colBest && r4cOff[p] < r4cOff[p - 1]) monotonic = false;
-        if (col4rowBest && c4rOff[p] < c4rOff[p - 1]) monotonic = false;
-        if (weightMode && probOff[p] < probOff[p - 1]) monotonic = false;
-    }
+    // transfers of one chunk overlap the kernel of another.  That needs the problems to lie one after the other in
+    // every array (then a chunk's inputs and outputs are contiguous ranges); otherwise, and for small batches, one chunk.
     // A chunk must stay large (>= 64k problems, ~18 per resident warp): every launch ends with a tail in which the
     // persistent warps run dry one by one, and at 12.5k problems per chunk that cost more than the overlap gained
     // (measured: 100k problems in 8 chunks, e2e 1.70 M/s vs 1.92 M/s unchunked).
-    const size_t nChunks = monotonic ? std::max<size_t>(1, std::min<size_t>(8, n / 65536)) : 1;
+    const size_t nChunks = contiguous ? std::max<size_t>(1, std::min<size_t>(8, n / 65536)) : 1;
     HostStreams* hs = nullptr;
     PDA_TRY(host_streams(device, &hs));
     cudaStream_t sIn = hs->in, sRun = hs->run, sOut = hs->out;
@@ -333,34 +347,33 @@ int pda_murty_batch_host(const double* costs, const int64_t* costOff, const int3
             const size_t p0 = n * c / nChunks, p1 = n * (c + 1) / nChunks, m = p1 - p0;
             const bool last = (p1 == n);
             // copy in: this chunk's cost matrices
-            const size_t c0 = nChunks == 1 ? 0 : (size_t)costOff[p0], c1 = (nChunks == 1 || last) ? nCost : (size_t)costOff[p1];
-            if (!costsDev) PDA_TRY(h2d(st.at<double>(oCost) + c0, costs + c0, c1 - c0, sIn));
+            const size_t c0 = nChunks == 1 ? rCost.lo : (size_t)costOff[p0], c1 = (nChunks == 1 || last) ? rCost.hi : (size_t)costOff[p1];
+            if (!costsDev) PDA_TRY(h2d(dCost + c0, costs + c0, c1 - c0, sIn));
             PDA_CUDA_TRY(cudaEventRecord(evIn[c], sIn));
             // run
             PDA_CUDA_TRY(cudaStreamWaitEvent(sRun, evIn[c], 0));
-            PDA_TRY(pda_murty_batch(costsDev ? costsDev : st.at<double>(oCost), st.at<int64_t>(oCostOff) + p0, st.at<int32_t>(oNR) + p0,
+            PDA_TRY(pda_murty_batch(dCost, st.at<int64_t>(oCostOff) + p0, st.at<int32_t>(oNR) + p0,
                                     st.at<int32_t>(oNC) + p0, (int64_t)m, maxR, maxC, k, cutMode, cutoff, maximize, cutMaximize,
-                                    row4colBest ? st.at<int64_t>(oR4c) : nullptr, st.at<int64_t>(oR4cOff) + p0,
-                                    col4rowBest ? st.at<int64_t>(oC4r) : nullptr, st.at<int64_t>(oC4rOff) + p0,
+                                    dR4c, st.at<int64_t>(oR4cOff) + p0, dC4r, st.at<int64_t>(oC4rOff) + p0,
                                     gainBest ? st.at<double>(oGain) + p0 * (size_t)k : nullptr, st.at<int32_t>(oFound) + p0,
-                                    weightMode, weightMode ? (probsDev ? probsDev : st.at<double>(oProb)) : nullptr,
-                                    st.at<int64_t>(oProbOff) + p0, st.at<int32_t>(oNL) + p0, st.at<unsigned char>(oWs), wsBytes, sRun));
+                                    weightMode, dProb, st.at<int64_t>(oProbOff) + p0, st.at<int32_t>(oNL) + p0,
+                                    st.at<unsigned char>(oWs), wsBytes, sRun));
             PDA_CUDA_TRY(cudaEventRecord(evRun[c], sRun));
             // copy out: this chunk's results
             PDA_CUDA_TRY(cudaStreamWaitEvent(sOut, evRun[c], 0));
             if (row4colBest) {
-                const size_t a0 = nChunks == 1 ? 0 : (size_t)r4cOff[p0], a1 = (nChunks == 1 || last) ? nR4c : (size_t)r4cOff[p1];
-                PDA_TRY(d2h(row4colBest + a0, st.at<int64_t>(oR4c) + a0, a1 - a0, sOut));
+                const size_t a0 = nChunks == 1 ? rR4c.lo : (size_t)r4cOff[p0], a1 = (nChunks == 1 || last) ? rR4c.hi : (size_t)r4cOff[p1];
+                PDA_TRY(d2h(row4colBest + a0, dR4c + a0, a1 - a0, sOut));
             }
             if (col4rowBest) {
-                const size_t a0 = nChunks == 1 ? 0 : (size_t)c4rOff[p0], a1 = (nChunks == 1 || last) ? nC4r : (size_t)c4rOff[p1];
-                PDA_TRY(d2h(col4rowBest + a0, st.at<int64_t>(oC4r) + a0, a1 - a0, sOut));
+                const size_t a0 = nChunks == 1 ? rC4r.lo : (size_t)c4rOff[p0], a1 = (nChunks == 1 || last) ? rC4r.hi : (size_t)c4rOff[p1];
+                PDA_TRY(d2h(col4rowBest + a0, dC4r + a0, a1 - a0, sOut));
             }
             if (gainBest) PDA_TRY(d2h(gainBest + p0 * (size_t)k, st.at<double>(oGain) + p0 * (size_t)k, m * (size_t)k, sOut));
             PDA_TRY(d2h(nFound + p0, st.at<int32_t>(oFound) + p0, m, sOut));
             if (weightMode && !probsDev) {
-                const size_t a0 = nChunks == 1 ? 0 : (size_t)probOff[p0], a1 = (nChunks == 1 || last) ? nProb : (size_t)probOff[p1];
-                PDA_TRY(d2h(probs + a0, st.at<double>(oProb) + a0, a1 - a0, sOut));
+                const size_t a0 = nChunks == 1 ? rProb.lo : (size_t)probOff[p0], a1 = (nChunks == 1 || last) ? rProb.hi : (size_t)probOff[p1];
+                PDA_TRY(d2h(probs + a0, dProb + a0, a1 - a0, sOut));
             }
         }
         PDA_CUDA_TRY(cudaStreamSynchronize(sOut));
@@ -369,8 +382,31 @@ int pda_murty_batch_host(const double* costs, const int64_t* costOff, const int3
         return PDA_OK;
     };
     rc = body();
+    if (rc != PDA_OK) { cudaStreamSynchronize(sIn); cudaStreamSynchronize(sRun); cudaStreamSynchronize(sOut); (void)cudaGetLastError(); }
     for (size_t c = 0; c < nChunks; ++c) { cudaEventDestroy(evIn[c]); cudaEventDestroy(evRun[c]); }
     return rc;
+}
+
+// One host thread per device, each running the single-device call on a contiguous slice of the batch (SURVEY.md 8e:
+// independent problems, no data-path collective, results land directly in the caller's arrays).
+int pda_murty_batch_host_multi(const double* costs, const int64_t* costOff, const int32_t* numRow, const int32_t* numCol,
+                               int64_t nProblems, int32_t k, int32_t cutMode, double cutoff, int32_t maximize,
+                               int32_t cutMaximize,
+                               int64_t* row4colBest, const int64_t* r4cOff,
+                               int64_t* col4rowBest, const int64_t* c4rOff,
+                               double* gainBest, int32_t* nFound,
+                               int32_t weightMode, double* probs, const int64_t* probOff, const int32_t* nL,
+                               const int32_t* devices, int32_t nDevices) {
+    if (!devices || nDevices < 1) return fail(PDA_ERR_INVALID, "murty (multi): need at least one device");
+    if (nProblems < 0) return fail(PDA_ERR_INVALID, "murty: nProblems < 0");
+    if (nProblems == 0) return PDA_OK;
+    if (!costs || !costOff || !numRow || !numCol || !nFound) return fail(PDA_ERR_INVALID, "murty: NULL input");
+    return run_sharded(nProblems, devices, nDevices, [&](int64_t p0, int64_t p1, int dev) {
+        return pda_murty_batch_host(costs, costOff + p0, numRow + p0, numCol + p0, p1 - p0, k, cutMode, cutoff, maximize, cutMaximize,
+                                    row4colBest, r4cOff ? r4cOff + p0 : nullptr, col4rowBest, c4rOff ? c4rOff + p0 : nullptr,
+                                    gainBest ? gainBest + p0 * (int64_t)k : nullptr, nFound + p0,
+                                    weightMode, probs, probOff ? probOff + p0 : nullptr, nL ? nL + p0 : nullptr, dev);
+    });
 }
 
 // ------------------------------------------------------------------------------------------- LAP
@@ -407,8 +443,8 @@ int pda_lap_batch_host(const double* costs, const int64_t* costOff, const int32_
         nRows = std::max(nRows, (size_t)rowOff[p] + r);
         nCols = std::max(nCols, (size_t)colOff[p] + c);
     }
-    std::lock_guard<std::mutex> lk(g_hostMu);
-    PDA_TRY(check_device(device));
+    DeviceScope scope;
+    PDA_TRY(scope.enter(device));
     const size_t n = (size_t)nProblems;
     Stage st(device);
     const size_t oCost = st.reserve(nCost * 8), oCostOff = st.reserve(n * 8), oNR = st.reserve(n * 4), oNC = st.reserve(n * 4);

@@ -12,6 +12,7 @@ namespace pda {
 // ---- error plumbing (pda_capi.cu) -------------------------------------------------------
 int fail(int code, const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
+unsigned long long failure_count();  // number of fail()/cuda_fail() calls made by this thread
 #define PDA_CUDA_TRY(expr)                                           \
     do {                                                             \
         cudaError_t _e = (expr);                                     \

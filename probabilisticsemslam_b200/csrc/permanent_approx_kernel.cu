@@ -211,8 +211,8 @@ int pda_permanent_approx_batch_host(const double* mats, const int64_t* matOff, c
         if (rows[i] < 0 || cols[i] < 0) return fail(PDA_ERR_INVALID, "permanent_approx: negative dimension");
         nEl = std::max(nEl, (size_t)matOff[i] + (size_t)rows[i] * cols[i]);
     }
-    std::lock_guard<std::mutex> lk(g_hostMu);
-    PDA_TRY(check_device(device));
+    DeviceScope scope;
+    PDA_TRY(scope.enter(device));
     const size_t n = (size_t)nMats;
     Stage st(device);
     PackedIO io(st);

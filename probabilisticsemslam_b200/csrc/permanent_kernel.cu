@@ -642,25 +642,27 @@ int pda_permanent_batch_host(const double* mats, const int64_t* matOff, const in
     if (nMats < 0) return fail(PDA_ERR_INVALID, "permanent: nMats < 0");
     if (nMats == 0) return PDA_OK;
     if (!mats || !matOff || !rows || !cols || !out) return fail(PDA_ERR_INVALID, "permanent: NULL argument");
-    size_t nEl = 0;
+    size_t nEl = 0, loEl = ~(size_t)0;  // only [loEl, nEl) of `mats` is staged (a shard passes the whole array)
     int maxDim = 0;
     for (int64_t i = 0; i < nMats; ++i) {
-        if (rows[i] < 0 || cols[i] < 0) return fail(PDA_ERR_INVALID, "permanent: negative dimension");
+        if (rows[i] < 0 || cols[i] < 0 || matOff[i] < 0) return fail(PDA_ERR_INVALID, "permanent: negative dimension or offset");
         nEl = std::max(nEl, (size_t)matOff[i] + (size_t)rows[i] * cols[i]);
+        loEl = std::min(loEl, (size_t)matOff[i]);
         maxDim = std::max(maxDim, std::max(rows[i], cols[i]));
     }
-    std::lock_guard<std::mutex> lk(g_hostMu);
-    PDA_TRY(check_device(device));
+    if (loEl > nEl) loEl = nEl;
+    DeviceScope scope;
+    PDA_TRY(scope.enter(device));
     DeviceInfo dev;
     PDA_TRY(current_device_info(&dev));
     const size_t n = (size_t)nMats;
     const size_t wsBytes = (size_t)pda_permanent_workspace_bytes(nMats);
     Stage st(device);
-    const size_t oM = st.reserve(nEl * 8), oOff = st.reserve(n * 8), oR = st.reserve(n * 4), oC = st.reserve(n * 4);
+    const size_t oM = st.reserve((nEl - loEl) * 8), oOff = st.reserve(n * 8), oR = st.reserve(n * 4), oC = st.reserve(n * 4);
     const size_t oOut = st.reserve(n * 8), oSt = st.reserve(n * 4), oWs = st.reserve(wsBytes);
     PDA_TRY(st.commit());
     cudaStream_t s = 0;
-    PDA_TRY(h2d(st.at<double>(oM), mats, nEl, s));
+    PDA_TRY(h2d(st.at<double>(oM), mats + loEl, nEl - loEl, s));
     PDA_TRY(h2d(st.at<int64_t>(oOff), matOff, n, s));
     PDA_TRY(h2d(st.at<int32_t>(oR), rows, n, s));
     PDA_TRY(h2d(st.at<int32_t>(oC), cols, n, s));
@@ -669,7 +671,7 @@ int pda_permanent_batch_host(const double* mats, const int64_t* matOff, const in
         const int sm = std::min(rows[i], cols[i]);
         maxSmall = std::max(maxSmall, sm); minSmall = std::min(minSmall, sm);
     }
-    PDA_TRY(launch_permanent_batch(st.at<double>(oM), st.at<int64_t>(oOff), st.at<int32_t>(oR), st.at<int32_t>(oC), nMats,
+    PDA_TRY(launch_permanent_batch(st.at<double>(oM) - loEl, st.at<int64_t>(oOff), st.at<int32_t>(oR), st.at<int32_t>(oC), nMats,
                                    maxDim, st.at<double>(oOut), st.at<int32_t>(oSt), st.at<unsigned char>(oWs),
                                    (int64_t)wsBytes, s, maxSmall, minSmall));
     PDA_TRY(d2h(out, st.at<double>(oOut), n, s));
@@ -693,8 +695,8 @@ int pda_permanent_range(const double* A, int32_t n, uint64_t begin, uint64_t end
 int pda_permanent_range_host(const double* A, int32_t n, uint64_t begin, uint64_t end, double* partial, int32_t device) {
     if (!A || !partial) return fail(PDA_ERR_INVALID, "permanent_range: NULL argument");
     if (n < 1 || n > PDA_MAX_PERM_DIM) return fail(PDA_ERR_UNSUPPORTED, "permanent_range: n = %d outside 1..%d", n, PDA_MAX_PERM_DIM);
-    std::lock_guard<std::mutex> lk(g_hostMu);
-    PDA_TRY(check_device(device));
+    DeviceScope scope;
+    PDA_TRY(scope.enter(device));
     DeviceInfo dev;
     PDA_TRY(current_device_info(&dev));
     const size_t wsBytes = 64 + (size_t)16 * 8192;
@@ -706,6 +708,49 @@ int pda_permanent_range_host(const double* A, int32_t n, uint64_t begin, uint64_
     PDA_TRY(pda_permanent_range(st.at<double>(oA), n, begin, end, st.at<double>(oP), st.at<unsigned char>(oWs), (int64_t)wsBytes, s));
     PDA_TRY(d2h(partial, st.at<double>(oP), 2, s));
     PDA_CUDA_TRY(cudaStreamSynchronize(s));
+    return PDA_OK;
+}
+
+// ---- multi-device forms: one host thread per device, no data-path collective except for the single
+// large permanent, whose 16-byte partial sums are gathered by the host and added in device order ----------------------
+int pda_permanent_batch_host_multi(const double* mats, const int64_t* matOff, const int32_t* rows, const int32_t* cols,
+                                   int64_t nMats, double* out, int32_t* status, const int32_t* devices, int32_t nDevices) {
+    if (!devices || nDevices < 1) return fail(PDA_ERR_INVALID, "permanent (multi): need at least one device");
+    if (nMats < 0) return fail(PDA_ERR_INVALID, "permanent: nMats < 0");
+    if (nMats == 0) return PDA_OK;
+    if (!mats || !matOff || !rows || !cols || !out || !status) return fail(PDA_ERR_INVALID, "permanent: NULL argument");
+    return run_sharded(nMats, devices, nDevices, [&](int64_t m0, int64_t m1, int dev) {
+        return pda_permanent_batch_host(mats, matOff + m0, rows + m0, cols + m0, m1 - m0, out + m0, status + m0, dev);
+    });
+}
+
+int pda_permanent_sharded_host(const double* A, int32_t n, const int32_t* devices, int32_t nDevices, double* out) {
+    if (!A || !out) return fail(PDA_ERR_INVALID, "permanent_sharded: NULL argument");
+    if (!devices || nDevices < 1) return fail(PDA_ERR_INVALID, "permanent_sharded: need at least one device");
+    if (n < 1 || n > PDA_MAX_PERM_DIM) return fail(PDA_ERR_UNSUPPORTED, "permanent_sharded: n = %d outside 1..%d", n, PDA_MAX_PERM_DIM);
+    // Gray index range [0, 2^(n-1)) in a power-of-two number of equal pieces: every boundary is a multiple of a large
+    // power of two, which keeps the kernel's column reads warp-uniform (launch_permanent_range)
+    const uint64_t total = 1ULL << (n - 1);
+    int parts = 1;
+    while (parts * 2 <= nDevices && (uint64_t)parts * 2 <= total) parts *= 2;
+    std::vector<double> partial((size_t)parts * 2, 0.0);
+    PDA_TRY(run_sharded(parts, devices, parts, [&](int64_t r0, int64_t r1, int dev) {
+        for (int64_t r = r0; r < r1; ++r) {
+            const int rc = pda_permanent_range_host(A, n, total * (uint64_t)r / parts, total * (uint64_t)(r + 1) / parts,
+                                                    partial.data() + 2 * r, dev);
+            if (rc) return rc;
+        }
+        return (int)PDA_OK;
+    }));
+    // (hi, lo) pairs added in device order: error-free two-sum on the high parts -- the result does not depend on timing
+    double hi = 0.0, lo = 0.0;
+    for (int r = 0; r < parts; ++r) {
+        const double h = partial[2 * (size_t)r], l = partial[2 * (size_t)r + 1];
+        const double s2 = hi + h, bb = s2 - hi, e = (hi - (s2 - bb)) + (h - bb);
+        hi = s2;
+        lo += e + l;
+    }
+    *out = (double)(4 * (n & 1) - 2) * (hi + lo);  // sign and factor 2 of the NW formula (nwPerm.cpp:326)
     return PDA_OK;
 }
 

@@ -314,8 +314,8 @@ int pda_conditioned_permanent_batch_host(const double* mats, const int64_t* matO
         nEl = std::max(nEl, (size_t)matOff[i] + (size_t)rows[i] * cols[i]);
         maxDim = std::max(maxDim, std::min(PDA_MAX_PERM_DIM, std::max(rows[i], cols[i])));
     }
-    std::lock_guard<std::mutex> lk(g_hostMu);
-    PDA_TRY(check_device(device));
+    DeviceScope scope;
+    PDA_TRY(scope.enter(device));
     const size_t n = (size_t)nMats;
     const size_t wsBytes = (size_t)pda_permanent_workspace_bytes(nMats);
     Stage st(device);
@@ -352,8 +352,8 @@ int pda_permanent_prob_batch_host(const double* costs, const int64_t* costOff, c
     const bool throws = (permOpt < 0 || permOpt > 2);
     // chunk the batch so that one chunk's items fit a bounded staging area
     const int64_t maxItemsPerChunk = 1 << 16;
-    std::lock_guard<std::mutex> lk(g_hostMu);
-    PDA_TRY(check_device(device));
+    DeviceScope scope;
+    PDA_TRY(scope.enter(device));
     int64_t p0 = 0;
     while (p0 < nProblems) {
         int64_t p1 = p0, items = 0;
@@ -431,6 +431,22 @@ int pda_permanent_prob_batch_host(const double* costs, const int64_t* costOff, c
         p0 = p1;
     }
     return PDA_OK;
+}
+
+int pda_permanent_prob_batch_host_multi(const double* costs, const int64_t* costOff, const int32_t* nL,
+                                        const int32_t* nM, int64_t nProblems, int32_t permOpt,
+                                        double* probs, const int64_t* probOff, int32_t* status,
+                                        const int32_t* devices, int32_t nDevices) {
+    if (!devices || nDevices < 1) return fail(PDA_ERR_INVALID, "permanent_prob (multi): need at least one device");
+    if (nProblems < 0) return fail(PDA_ERR_INVALID, "permanent_prob: nProblems < 0");
+    if (nProblems == 0) return PDA_OK;
+    if (!costs || !costOff || !nL || !nM || !probs || !probOff || !status) return fail(PDA_ERR_INVALID, "permanent_prob: NULL argument");
+    // the (nL+1) * nM sub-permanents of a problem are independent (assignment.cpp:213-246), and so are the problems:
+    // contiguous slices of problems, one per device
+    return run_sharded(nProblems, devices, nDevices, [&](int64_t p0, int64_t p1, int dev) {
+        return pda_permanent_prob_batch_host(costs, costOff + p0, nL + p0, nM + p0, p1 - p0, permOpt, probs, probOff + p0,
+                                             status + p0, dev);
+    });
 }
 
 }  // extern "C"

@@ -155,8 +155,8 @@ int pda_quadric_covs_batch_host(const double* quadrics, int64_t n, double* covs,
     if (n < 0) return fail(PDA_ERR_INVALID, "quadric_covs: n < 0");
     if (n == 0) return PDA_OK;
     if (!quadrics || !covs) return fail(PDA_ERR_INVALID, "quadric_covs: NULL argument");
-    std::lock_guard<std::mutex> lk(g_hostMu);
-    PDA_TRY(check_device(device));
+    DeviceScope scope;
+    PDA_TRY(scope.enter(device));
     Stage st(device);
     const size_t oQ = st.reserve((size_t)n * 16 * 8), oC = st.reserve((size_t)n * 9 * 8);
     PDA_TRY(st.commit());
@@ -211,8 +211,8 @@ int pda_quadric_cost_batch_host(const double* landMean, const double* landCov, c
     PDA_TRY(quadric_shapes(landOff, measOff, nFrames, costOff, probOff, rowOff, nCost, nProb, nRows, maxR, maxC));
     const size_t n = (size_t)nFrames, nLand = (size_t)landOff[n], nMeas = (size_t)measOff[n];
     if ((nLand && (!landMean || !landCov)) || (nMeas && (!measMean || !measCov))) return fail(PDA_ERR_INVALID, "quadric_cost: NULL moments");
-    std::lock_guard<std::mutex> lk(g_hostMu);
-    PDA_TRY(check_device(device));
+    DeviceScope scope;
+    PDA_TRY(scope.enter(device));
     Stage st(device);
     PackedIO io(st);
     const size_t oLM = io.in(landMean, nLand * 24), oLC = io.in(landCov, nLand * 72), oLO = io.in(landOff, (n + 1) * 8);
@@ -245,8 +245,8 @@ int pda_association_from_moments_batch_host(const double* landMean, const double
     const size_t n = (size_t)nFrames, nLand = (size_t)landOff[n], nMeas = (size_t)measOff[n];
     if ((nLand && (!landMean || !landCov)) || (nMeas && (!measMean || !measCov))) return fail(PDA_ERR_INVALID, "association_from_moments: NULL moments");
     if (nProb == 0) return PDA_OK;
-    std::lock_guard<std::mutex> lk(g_hostMu);
-    PDA_TRY(check_device(device));
+    DeviceScope scope;
+    PDA_TRY(scope.enter(device));
     const int64_t wsBytes = pda_association_workspace_bytes(nFrames, (int64_t)nCost, (int64_t)nRows, (int64_t)nProb, k, maxR, maxC);
     if (wsBytes < 0) return (int)wsBytes;
     Stage st(device);

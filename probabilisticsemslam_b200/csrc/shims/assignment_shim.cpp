@@ -197,29 +197,86 @@ double permanentExactRaw(const double* A, size_t rows, size_t cols) {
 
 long double permanentExactLongRaw(const double* A, size_t rows, size_t cols) { return permanentExactRaw(A, rows, cols); }
 
+namespace {
+// flat, offset-addressed form of a vector-of-problems batch (what the C ABI takes)
+struct FlatBatch {
+    std::vector<int64_t> costOff, probOff;
+    std::vector<int32_t> nr, nc, nl;
+    std::vector<double> flat, probs;
+    FlatBatch(const std::vector<std::vector<double> >& costs, const std::vector<size_t>& nL, const std::vector<size_t>& nM) {
+        const size_t n = costs.size();
+        costOff.resize(n); probOff.resize(n); nr.resize(n); nc.resize(n); nl.resize(n);
+        size_t nCost = 0, nProb = 0;
+        for (size_t p = 0; p < n; p++) {
+            if (costs[p].size() != (nL[p] + nM[p]) * nM[p]) throw std::invalid_argument("batch: cost matrix size does not match (nL + nM) * nM");
+            costOff[p] = int64_t(nCost); probOff[p] = int64_t(nProb);
+            nr[p] = int32_t(nL[p] + nM[p]); nc[p] = int32_t(nM[p]); nl[p] = int32_t(nL[p]);
+            nCost += costs[p].size(); nProb += nM[p] * (nL[p] + 1);
+        }
+        flat.resize(nCost ? nCost : 1); probs.resize(nProb ? nProb : 1);
+        for (size_t p = 0; p < n; p++) std::copy(costs[p].begin(), costs[p].end(), flat.begin() + costOff[p]);
+    }
+    std::vector<std::vector<std::vector<double> > > tables(const std::vector<size_t>& nL, const std::vector<size_t>& nM) const {
+        std::vector<std::vector<std::vector<double> > > out(nr.size());
+        for (size_t p = 0; p < nr.size(); p++) {
+            std::vector<double> slice(probs.begin() + probOff[p], probs.begin() + probOff[p] + nM[p] * (nL[p] + 1));
+            out[p] = unflatten(slice, nM[p], nL[p] + 1);
+        }
+        return out;
+    }
+};
+std::vector<int32_t> deviceList(const std::vector<int>& devices) {
+    std::vector<int32_t> d(devices.begin(), devices.end());
+    if (d.empty()) d.push_back(pdaShimDevice());
+    return d;
+}
+}  // namespace
+
+std::vector<std::vector<std::vector<double> > > assignmentProbBatch(const std::vector<std::vector<double> >& costs,
+                                                                    const std::vector<size_t>& nL,
+                                                                    const std::vector<size_t>& nM, size_t k,
+                                                                    const std::vector<int>& devices) {
+    FlatBatch fb(costs, nL, nM);
+    const size_t n = costs.size();
+    std::vector<int32_t> found(n ? n : 1);
+    const std::vector<int32_t> dev = deviceList(devices);
+    if (n)
+        pdaCheck(pda_murty_batch_host_multi(fb.flat.data(), fb.costOff.data(), fb.nr.data(), fb.nc.data(), int64_t(n), int32_t(k),
+                                            PDA_CUT_RELATIVE, 42.0, 0, 0, NULL, NULL, NULL, NULL, NULL, found.data(),
+                                            PDA_WEIGHTS_GATED, fb.probs.data(), fb.probOff.data(), fb.nl.data(), dev.data(),
+                                            int32_t(dev.size())),
+                 "assignmentProbBatch");
+    return fb.tables(nL, nM);
+}
+
 std::vector<std::vector<std::vector<double> > > assignmentProbBatch(const std::vector<std::vector<double> >& costs,
                                                                     const std::vector<size_t>& nL,
                                                                     const std::vector<size_t>& nM, size_t k) {
+    return assignmentProbBatch(costs, nL, nM, k, std::vector<int>());
+}
+
+std::vector<std::vector<std::vector<double> > > permanentProbBatch(const std::vector<std::vector<double> >& costs,
+                                                                   const std::vector<size_t>& nL,
+                                                                   const std::vector<size_t>& nM, int permOpt,
+                                                                   const std::vector<int>& devices) {
+    FlatBatch fb(costs, nL, nM);
     const size_t n = costs.size();
-    std::vector<int64_t> costOff(n), probOff(n);
-    std::vector<int32_t> nr(n), nc(n), nl(n), found(n);
-    size_t nCost = 0, nProb = 0;
-    for (size_t p = 0; p < n; p++) {
-        costOff[p] = int64_t(nCost); probOff[p] = int64_t(nProb);
-        nr[p] = int32_t(nL[p] + nM[p]); nc[p] = int32_t(nM[p]); nl[p] = int32_t(nL[p]);
-        nCost += costs[p].size(); nProb += nM[p] * (nL[p] + 1);
-    }
-    std::vector<double> flat(nCost ? nCost : 1), probs(nProb ? nProb : 1);
-    for (size_t p = 0; p < n; p++) std::copy(costs[p].begin(), costs[p].end(), flat.begin() + costOff[p]);
+    std::vector<int32_t> status(n ? n : 1, 0);
+    const std::vector<int32_t> dev = deviceList(devices);
     if (n)
-        pdaCheck(pda_murty_batch_host(flat.data(), costOff.data(), nr.data(), nc.data(), int64_t(n), int32_t(k), PDA_CUT_RELATIVE,
-                                      42.0, 0, 0, NULL, NULL, NULL, NULL, NULL, found.data(), PDA_WEIGHTS_GATED, probs.data(),
-                                      probOff.data(), nl.data(), pdaShimDevice()),
-                 "assignmentProbBatch");
-    std::vector<std::vector<std::vector<double> > > out(n);
-    for (size_t p = 0; p < n; p++) {
-        std::vector<double> slice(probs.begin() + probOff[p], probs.begin() + probOff[p] + nM[p] * (nL[p] + 1));
-        out[p] = unflatten(slice, nM[p], nL[p] + 1);
-    }
+        pdaCheck(pda_permanent_prob_batch_host_multi(fb.flat.data(), fb.costOff.data(), fb.nl.data(), fb.nc.data(), int64_t(n), permOpt,
+                                                     fb.probs.data(), fb.probOff.data(), status.data(), dev.data(), int32_t(dev.size())),
+                 "permanentProbBatch");
+    for (size_t p = 0; p < n; p++)
+        if (status[p]) throw std::runtime_error("permanentProbBatch: the reference throws for one of these problems (dimension > 32 or bad permOpt)");
+    return fb.tables(nL, nM);
+}
+
+double permanentExactShardedRaw(const double* A, size_t n, const int* devices, size_t nDevices) {
+    if (n > 32) throw std::runtime_error("Maximum matrix dimension limited to 32. Error inside permanentExactSquare().");
+    std::vector<int32_t> dev(devices, devices + nDevices);
+    if (dev.empty()) dev.push_back(pdaShimDevice());
+    double out = 0;
+    pdaCheck(pda_permanent_sharded_host(A, int32_t(n), dev.data(), int32_t(dev.size()), &out), "permanentExactSharded");
     return out;
 }

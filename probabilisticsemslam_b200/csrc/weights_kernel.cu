@@ -150,8 +150,8 @@ int pda_condition_costs_batch_host(const double* costs, const int64_t* costOff, 
         nCost = std::max(nCost, (size_t)costOff[p] + (size_t)r * c);
         nRows = std::max(nRows, (size_t)rowOff[p] + r);
     }
-    std::lock_guard<std::mutex> lk(g_hostMu);
-    PDA_TRY(check_device(device));
+    DeviceScope scope;
+    PDA_TRY(scope.enter(device));
     const size_t n = (size_t)nProblems;
     Stage st(device);
     const size_t oC = st.reserve(nCost * 8), oCO = st.reserve(n * 8), oNR = st.reserve(n * 4), oNC = st.reserve(n * 4);
@@ -186,8 +186,8 @@ int pda_to_probs_batch_host(double* values, const int64_t* off, const int64_t* l
     if (!values || !off || !len) return fail(PDA_ERR_INVALID, "to_probs: NULL argument");
     size_t total = 0;
     for (int64_t i = 0; i < nVectors; ++i) total = std::max(total, (size_t)(off[i] + len[i]));
-    std::lock_guard<std::mutex> lk(g_hostMu);
-    PDA_TRY(check_device(device));
+    DeviceScope scope;
+    PDA_TRY(scope.enter(device));
     const size_t n = (size_t)nVectors;
     Stage st(device);
     const size_t oV = st.reserve(total * 8), oO = st.reserve(n * 8), oL = st.reserve(n * 8);

@@ -89,10 +89,11 @@ def _rel(a, b):
 
 
 def test_permanent_prob_golden_and_oracle(gpu_api, oracle):
-    """Permanent-based weights on gated (sparse, wide-dynamic-range) problems.  The NW sum cancels, and on
-    some of these inputs the REFERENCE is itself only ~1e-8 accurate, so each result is
-    judged against a cancellation-free truth (tests/truth.py): within 1e-9 of the reference wherever
-    the reference is accurate, and never worse than a small multiple of the reference's own error."""
+    """Permanent-based weights on gated (sparse, wide-dynamic-range) problems.  The reference's NW sum over the
+    ones-padded matrix cancels, and on some of these inputs the REFERENCE is itself only ~1e-8 accurate (SURVEY.md
+    F5).  The device evaluates these short-sided sub-permanents by a subset dynamic programme with non-negative
+    terms only (perm_dp_warp), so every table must be within 1e-9 of the cancellation-free truth (tests/truth.py),
+    and within 1e-9 of the reference wherever the reference's own error is below 1e-10."""
     from truth import permanent_prob_truth
     z = golden("weights_g2cond")
     for p in range(int(z["n"])):
@@ -100,7 +101,7 @@ def test_permanent_prob_golden_and_oracle(gpu_api, oracle):
             got = gpu_api.permanentProb(z[f"C{p}"], int(z[f"nL{p}"]), 1)
             truth = permanent_prob_truth(z[f"C{p}"], int(z[f"nL{p}"]))
             ref_err = _rel(z[f"pp_{p}"], truth)
-            assert _rel(got, truth) <= max(RTOL, 8 * ref_err)
+            assert _rel(got, truth) <= RTOL
             if ref_err < 1e-10:
                 np.testing.assert_allclose(got, z[f"pp_{p}"], rtol=RTOL, atol=1e-300)
     g2 = synth.g2_gated(80, first=500)
@@ -115,7 +116,7 @@ def test_permanent_prob_golden_and_oracle(gpu_api, oracle):
         assert st[i] == s == 0
         truth = permanent_prob_truth(sub.matrix(i), int(sub.nL[i]))
         ref_err = _rel(want, truth)
-        assert _rel(tabs[i], truth) <= max(RTOL, 8 * ref_err), (i, _rel(tabs[i], truth), ref_err)
+        assert _rel(tabs[i], truth) <= RTOL, (i, _rel(tabs[i], truth), ref_err)
         if ref_err < 1e-10:
             n_tight += 1
             np.testing.assert_allclose(tabs[i], want, rtol=RTOL, atol=1e-300)

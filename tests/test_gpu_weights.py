@@ -87,8 +87,20 @@ def test_association_probs_fused_pipeline(gpu_api, oracle):
     for p in range(n):
         np.testing.assert_allclose(tabs[p], z[f"k200_{p}"], rtol=RTOL, atol=0)
         if f"perm_{p}" in z:
+            # usePerm: conditionCosts -> permanentProb -> scatter.  Judged against the cancellation-free truth at 1e-9,
+            # and against the reference's own table wherever that is itself accurate (see test_gpu_permanent).
+            from truth import permanent_prob_truth
             got = gpu_api.getAssignmentProbsFromCosts(z[f"C{p}"], 30, 200, usePerm=True)
-            np.testing.assert_allclose(got, z[f"perm_{p}"], rtol=1e-6, atol=1e-300)   # NW cancellation: see test_gpu_permanent
+            cond, rows = gpu_api.conditionCosts(z[f"C{p}"])
+            nM, condL = cond.shape[1], cond.shape[0] - cond.shape[1]
+            tc = permanent_prob_truth(cond, condL)
+            truth = np.zeros((nM, 31))
+            truth[:, rows[:condL]] = tc[:, :condL]
+            truth[:, 30] = tc[:, condL]
+            np.testing.assert_allclose(got, truth, rtol=RTOL, atol=1e-300)
+            m = truth > 0
+            if np.max(np.abs(z[f"perm_{p}"][m] - truth[m]) / truth[m]) < 1e-10:
+                np.testing.assert_allclose(got, z[f"perm_{p}"], rtol=RTOL, atol=1e-300)
     # a bigger ragged batch against the oracle, including problems without landmarks and with one detection
     g2 = synth.g2_gated(300, first=4000)
     mats = [g2.matrix(p) for p in range(300)] + [np.array([[10.0, np.inf], [np.inf, 10.0]]), np.array([[3.0], [50.0], [10.0]])]
