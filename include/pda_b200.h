@@ -76,6 +76,15 @@ double pda_diag_dfma_tflops(void);
  */
 int64_t pda_murty_workspace_bytes(int64_t nProblems, int32_t k, int32_t maxNumRow, int32_t maxNumCol);
 
+/* Page-locked host buffers for the *_host entry points.  A *_host call that finds its large arrays (cost matrices in,
+ * weight tables out) page-locked uses them IN PLACE: every warp reads its cost matrix and writes its weight table over
+ * the bus itself, so the transfers hide under the computing instead of standing in front of and behind the kernel.
+ * Buffers from pda_host_alloc are portable: every device of the process may use them in place (the multi-device
+ * entry points below).  Memory the caller pinned itself (cudaHostAlloc / cudaHostRegister) is used in place only by the
+ * device whose context pinned it; pageable memory is copied.  Returns NULL on failure (pda_last_error). */
+void* pda_host_alloc(int64_t bytes);
+void pda_host_free(void* p);
+
 /* Three kernels stand behind pda_murty_batch, with bit-identical results: one WARP per problem, exact (the
  * reference's heap order replayed; always right), one WARP per problem, FAST (large batches: hypotheses that provably
  * cannot be among the k best are abandoned early and the open list is a warp-parallel queue; a problem in which two

@@ -19,6 +19,8 @@ SIGNATURES = {
     "pda_last_error": (C.c_char_p, []),
     "pda_device_count": (C.c_int, []),
     "pda_diag_dfma_tflops": (dbl, []),
+    "pda_host_alloc": (ptr, [i64]),
+    "pda_host_free": (None, [ptr]),
     "pda_murty_workspace_bytes": (i64, [i64, i32, i32, i32]),
     "pda_murty_set_path": (C.c_int, [i32]),
     "pda_murty_batch": (C.c_int, [ptr, ptr, ptr, ptr, i64, i32, i32, i32, i32, dbl, i32, i32,

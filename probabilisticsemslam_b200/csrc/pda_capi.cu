@@ -110,15 +110,45 @@ int pda_device_count(void) {
     return n;
 }
 
+// Page-locked buffers handed out by pda_host_alloc: allocated portable + mapped, so EVERY device may use them in place.
+static std::mutex g_pinMu;
+static std::vector<std::pair<const unsigned char*, size_t> > g_pinRanges;
+static bool in_portable_range(const void* p) {
+    std::lock_guard<std::mutex> lk(g_pinMu);
+    for (const auto& r : g_pinRanges)
+        if ((const unsigned char*)p >= r.first && (const unsigned char*)p < r.first + r.second) return true;
+    return false;
+}
+
+void* pda_host_alloc(int64_t bytes) {
+    if (bytes <= 0) { fail(PDA_ERR_INVALID, "pda_host_alloc: bytes <= 0"); return nullptr; }
+    void* p = nullptr;
+    const cudaError_t e = cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocPortable | cudaHostAllocMapped);
+    if (e != cudaSuccess) { cuda_fail(e, "cudaHostAlloc(pda_host_alloc)"); return nullptr; }
+    std::lock_guard<std::mutex> lk(g_pinMu);
+    g_pinRanges.push_back(std::make_pair((const unsigned char*)p, (size_t)bytes));
+    return p;
+}
+void pda_host_free(void* p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(g_pinMu);
+        for (size_t i = 0; i < g_pinRanges.size(); ++i)
+            if (g_pinRanges[i].first == (const unsigned char*)p) { g_pinRanges.erase(g_pinRanges.begin() + (long)i); break; }
+    }
+    cudaFreeHost(p);
+}
+
 // If `p` is page-locked host memory that the device can address (cudaHostAlloc / cudaHostRegister under unified
 // addressing), returns the device-side alias, else NULL.
 static void* mapped_alias(const void* p, int device) {
     if (!p) return nullptr;
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
-    // page-locked by a context of THIS device (memory pinned for another device's context is only guaranteed to be
-    // addressable there unless it was allocated portable: take the copying path for it)
-    return (at.type == cudaMemoryTypeHost && at.device == device) ? at.devicePointer : nullptr;
+    // page-locked by a context of THIS device, or handed out by pda_host_alloc (portable).  Memory pinned for another
+    // device's context by somebody else is only guaranteed to be addressable there: take the copying path for it.
+    if (at.type != cudaMemoryTypeHost) return nullptr;
+    return (at.device == device || in_portable_range(p)) ? at.devicePointer : nullptr;
 }
 
 // ---------------------------------------------------------------------------------------- Murty

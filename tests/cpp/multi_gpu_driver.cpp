@@ -5,6 +5,7 @@
 // A device may be listed more than once (its slices then queue on that device's lock), so the sharding logic can be
 // checked on a single-GPU box.  Prints one JSON line: throughputs on the first device alone and on all of them, and
 // whether the sharded results are bit-identical to the single-device ones.
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -16,6 +17,7 @@
 
 #include "assignment.h"
 #include "nwPerm.h"
+#include "pda_b200.h"
 
 static uint64_t mix(uint64_t z) {
     z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ULL; z ^= z >> 27; z *= 0x94D049BB133111EBULL; z ^= z >> 31;
@@ -54,25 +56,63 @@ int main(int argc, char** argv) {
             pos = q + 1;
         }
     }
-    std::vector<std::vector<double> > costs(nProb);
+    // ---- the batch in the flat layout of the C ABI, in page-locked buffers every device may use in place ------------
+    std::vector<int64_t> costOff(nProb), probOff(nProb);
+    std::vector<int32_t> nr(nProb), nc(nProb), nl(nProb);
     std::vector<size_t> nL(nProb), nM(nProb);
-    for (size_t p = 0; p < nProb; p++) g1(p, costs[p], nL[p], nM[p]);
-    const std::vector<int> one(1, devices[0]);
-
-    // ---- k-best association weights: one device, then all of them ------------------------------------------------
-    assignmentProbBatch(costs, nL, nM, k, devices);  // warm-up (arenas, streams, module load) on every device
-    double t0 = now();
-    const std::vector<std::vector<std::vector<double> > > single = assignmentProbBatch(costs, nL, nM, k, one);
-    const double tSingle = now() - t0;
-    t0 = now();
-    const std::vector<std::vector<std::vector<double> > > multi = assignmentProbBatch(costs, nL, nM, k, devices);
-    const double tMulti = now() - t0;
-    bool same = single.size() == multi.size();
-    for (size_t p = 0; same && p < nProb; p++)
-        for (size_t m = 0; same && m < nM[p]; m++)
-            same = memcmp(single[p][m].data(), multi[p][m].data(), sizeof(double) * (nL[p] + 1)) == 0;
+    size_t nCost = 0, nPr = 0;
+    {
+        std::vector<double> tmp;
+        for (size_t p = 0; p < nProb; p++) {
+            g1(p, tmp, nL[p], nM[p]);
+            costOff[p] = (int64_t)nCost; probOff[p] = (int64_t)nPr;
+            nr[p] = (int32_t)(nL[p] + nM[p]); nc[p] = (int32_t)nM[p]; nl[p] = (int32_t)nL[p];
+            nCost += tmp.size(); nPr += nM[p] * (nL[p] + 1);
+        }
+    }
+    double* costs = (double*)pda_host_alloc((int64_t)nCost * 8);
+    double* probs1 = (double*)pda_host_alloc((int64_t)nPr * 8);
+    double* probsN = (double*)pda_host_alloc((int64_t)nPr * 8);
+    int32_t* found = (int32_t*)pda_host_alloc((int64_t)nProb * 4);
+    if (!costs || !probs1 || !probsN || !found) { fprintf(stderr, "pda_host_alloc: %s\n", pda_last_error()); return 2; }
+    {
+        std::vector<double> tmp;
+        size_t a, b;
+        for (size_t p = 0; p < nProb; p++) { g1(p, tmp, a, b); memcpy(costs + costOff[p], tmp.data(), tmp.size() * 8); }
+    }
+    std::vector<int32_t> dev32(devices.begin(), devices.end());
+    auto run = [&](double* probs, const int32_t* dev, int nDev) {
+        const int rc = pda_murty_batch_host_multi(costs, costOff.data(), nr.data(), nc.data(), (int64_t)nProb, (int32_t)k,
+                                                  PDA_CUT_RELATIVE, 42.0, 0, 0, NULL, NULL, NULL, NULL, NULL, found,
+                                                  PDA_WEIGHTS_GATED, probs, probOff.data(), nl.data(), dev, nDev);
+        if (rc) { fprintf(stderr, "pda_murty_batch_host_multi: %s\n", pda_last_error()); exit(2); }
+    };
+    run(probsN, dev32.data(), (int)dev32.size());  // warm-up (arenas, streams, module load) on every device
+    double tSingle = 1e30, tMulti = 1e30;
+    for (int rep = 0; rep < 3; rep++) {
+        double t0 = now();
+        run(probs1, dev32.data(), 1);
+        tSingle = std::min(tSingle, now() - t0);
+        t0 = now();
+        run(probsN, dev32.data(), (int)dev32.size());
+        tMulti = std::min(tMulti, now() - t0);
+    }
+    bool same = memcmp(probs1, probsN, nPr * 8) == 0;
     double checksum = 0;
-    for (size_t p = 0; p < nProb; p++) checksum += multi[p][0][0];
+    for (size_t p = 0; p < nProb; p++) checksum += probsN[probOff[p]];
+
+    // ---- the std::vector face of the same call (include/assignment.h), on a slice ------------------------------------
+    {
+        const size_t m = std::min<size_t>(nProb, 1500);
+        std::vector<std::vector<double> > vc(m);
+        std::vector<size_t> vL(nL.begin(), nL.begin() + (long)m), vM(nM.begin(), nM.begin() + (long)m);
+        for (size_t p = 0; p < m; p++) vc[p].assign(costs + costOff[p], costs + costOff[p] + (size_t)nr[p] * nc[p]);
+        const std::vector<std::vector<std::vector<double> > > tabs = assignmentProbBatch(vc, vL, vM, k, devices);
+        for (size_t p = 0; same && p < m; p++)
+            for (size_t c = 0; same && c < vM[p]; c++)
+                same = memcmp(tabs[p][c].data(), probsN + probOff[p] + c * (vL[p] + 1), sizeof(double) * (vL[p] + 1)) == 0;
+    }
+    const std::vector<int> one(1, devices[0]);
 
     // ---- permanent weights of small gated problems (config 4), sharded the same way -----------------------------
     const size_t nPerm = std::min<size_t>(nProb, 256);
@@ -100,7 +140,7 @@ int main(int argc, char** argv) {
     for (size_t i = 0; i < A.size(); i++) A[i] = u01(mix(((GAMMA * 4243ULL) ^ SEED) + (uint64_t)(i + 1) * GAMMA));
     const double whole = permanentExactRaw(A.data(), permDim, permDim);
     permanentExactShardedRaw(A.data(), permDim, devices.data(), devices.size());
-    t0 = now();
+    double t0 = now();
     const double sharded = permanentExactShardedRaw(A.data(), permDim, devices.data(), devices.size());
     const double tPerm = now() - t0;
 
@@ -109,5 +149,6 @@ int main(int argc, char** argv) {
            "\"perm_dim\": %zu, \"perm_whole\": %.17g, \"perm_sharded\": %.17g, \"perm_rel_diff\": %.3g, \"perm_sharded_ms\": %.4f}\n",
            nProb, k, devices.size(), nProb / tSingle, nProb / tMulti, tSingle / tMulti, same ? "true" : "false", checksum,
            samePerm ? "true" : "false", permDim, whole, sharded, std::fabs(sharded - whole) / std::fabs(whole), tPerm * 1e3);
+    pda_host_free(costs); pda_host_free(probs1); pda_host_free(probsN); pda_host_free(found);
     return (same && samePerm) ? 0 : 1;
 }
