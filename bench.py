@@ -51,7 +51,7 @@ def measured_traffic(n, k):
     when it was taken at this problem count; None otherwise."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            t = json.load(f)["murty_kernel<2>"]
+            t = json.load(f)["murty_kernel<2, true>"]
         return t["dram_bytes"] if (t["problems"] == n and t["k"] == k) else None
     except (OSError, KeyError, ValueError):
         return None
@@ -175,6 +175,8 @@ def main():
     ap.add_argument("--problems", type=int, default=N_PER_GPU, help="problems per GPU (default: the BASELINE configuration)")
     ap.add_argument("--k", type=int, default=K_BEST)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--skip-config3", action="store_true", help="skip extra.config3_k1000_strong (profiling runs)")
+    ap.add_argument("--skip-config4", action="store_true", help="skip extra.permanent_batch_sharded (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -224,6 +226,7 @@ def main():
     value = world * n * args.steps / (total_ms_max * 1e-3)
     alg_bytes = plan.algorithmic_bytes()
     kernel_ms = statistics.mean(step_ms)
+    fallback_problems = int(plan.workspace[8:12].view(torch.int32).item())  # problems the pruning kernel handed to the exact one
 
     # ---- end to end: host buffers through the C ABI (batched assignmentProb) ----------------------------
     nL32, nM32 = pb.nL.astype(np.int32), pb.nM.astype(np.int32)
@@ -257,6 +260,45 @@ def main():
     d2h = int(h_probs.numel() * 8 + h_found.numel() * 4)
     probs_dev = plan.probs.cpu().numpy()
     e2e_matches = bool(np.array_equal(probs_dev, h_probs.numpy()))
+
+    # ---- e2e variants (rank 0 of a single-GPU run): the same host call with PAGEABLE buffers (copied through the
+    #      staging arena), and kBest2DCutoff semantics -- every k-best list and gain returned to the host -- on 20 000
+    #      problems with page-locked buffers (1.3 GB of lists per pass cross the bus device -> host)
+    e2e_variants = None
+    if world == 1:
+        pg_costs, pg_probs, pg_found = pb.costs.copy(), np.zeros(plan.n_prob), np.zeros(n, np.int32)
+        def pageable_step():
+            _lib.check(lib.pda_murty_batch_host(pg_costs.ctypes.data, pb.cost_off.ctypes.data, nR32.ctypes.data, nM32.ctypes.data, n, k,
+                                                1, 42.0, 0, 0, None, None, None, None, None, pg_found.ctypes.data,
+                                                1, pg_probs.ctypes.data, prob_off.ctypes.data, nL32.ctypes.data, local))
+        pageable_step()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            pageable_step()
+        pageable_pps = 2 * n / (time.perf_counter() - t0)
+        nl_ = min(n, 20000)
+        r4o, c4o = plan.r4c_off_h[:nl_], plan.c4r_off_h[:nl_]
+        n_r4c = int(nM32[:nl_].astype(np.int64).sum()) * k
+        n_c4r = int(nR32[:nl_].astype(np.int64).sum()) * k
+        hl_r4c = torch.empty(n_r4c, dtype=torch.int64).pin_memory()
+        hl_c4r = torch.empty(n_c4r, dtype=torch.int64).pin_memory()
+        hl_gain = torch.empty(nl_ * k, dtype=torch.float64).pin_memory()
+        def lists_step():
+            _lib.check(lib.pda_murty_batch_host(h_costs.data_ptr(), h_off.data_ptr(), h_nr.data_ptr(), h_nc.data_ptr(), nl_, k,
+                                                1, 42.0, 0, 0, hl_r4c.data_ptr(), r4o.ctypes.data, hl_c4r.data_ptr(), c4o.ctypes.data,
+                                                hl_gain.data_ptr(), h_found.data_ptr(), 1, h_probs.data_ptr(), h_poff.data_ptr(),
+                                                h_nl.data_ptr(), local))
+        lists_step()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            lists_step()
+        lists_pps = 2 * nl_ / (time.perf_counter() - t0)
+        e2e_variants = {"pageable_buffers_weights_only": {"value": pageable_pps, "unit": UNIT, "problems": n,
+                                                          "note": "numpy arrays: inputs and outputs are copied through the staging arena"},
+                        "lists_to_host_kBest2DCutoff": {"value": lists_pps, "unit": UNIT, "problems": nl_,
+                                                        "d2h_bytes_per_pass": int((n_r4c + n_c4r + nl_ * k) * 8),
+                                                        "note": "row4col + col4row (int64) + gains of every hypothesis returned to page-locked host buffers"}}
+        del hl_r4c, hl_c4r, hl_gain
 
     # ---- permanent n = 24 latency (second half of the metric) ----------------------------------------------
     A24 = synth.dense_square(1, 24, first=4242)
@@ -298,6 +340,118 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     perm28_ms = float(t.item())
     perm28_value = shard.combine_partials(parts.cpu().numpy(), 28)
+
+    # ---- config 3 as BASELINE words it: the SAME 100k-problem batch at k = 1000, cut into contiguous slices over the
+    #      ranks (strong scaling).  Lists, gains and weights are written on the owning rank; the weight tables and
+    #      nFound are gathered on rank 0 inside the timed region (assignmentProb's result; the 33 GB of k-best lists
+    #      stay where they were produced).  Time = max over ranks.  Present at every N, so the driver's scaling file
+    #      carries a strong-scaling series next to the weak-scaling headline.
+    cfg3 = None
+    if not args.skip_config3:
+        k3, n3 = 1000, args.problems
+        lo3, hi3 = n3 * rank // world, n3 * (rank + 1) // world
+        torch.cuda.empty_cache()
+        pb3 = synth.g1_dense(hi3 - lo3, first=lo3)
+        plan3 = dev.MurtyPlan(pb3, k=k3, weights=True)
+        sizes3 = [n3 * (r + 1) // world - n3 * r // world for r in range(world)]
+        # gather buffers on rank 0: equal-sized slots (the largest slice's table), plain NCCL gather
+        slot = torch.tensor([plan3.n_prob], dtype=torch.int64, device="cuda")
+        if world > 1:
+            dist.all_reduce(slot, op=dist.ReduceOp.MAX)
+        slot = int(slot.item())
+        send_p = torch.zeros(slot, dtype=torch.float64, device="cuda")
+        send_f = torch.zeros(max(sizes3), dtype=torch.int32, device="cuda")
+        recv_p = [torch.empty(slot, dtype=torch.float64, device="cuda") for _ in range(world)] if rank == 0 else None
+        recv_f = [torch.empty(max(sizes3), dtype=torch.int32, device="cuda") for _ in range(world)] if rank == 0 else None
+        def cfg3_step():
+            plan3.run()
+            if world > 1:
+                send_p[:plan3.n_prob].copy_(plan3.probs)
+                send_f[:plan3.n].copy_(plan3.n_found)
+                dist.gather(send_p, recv_p, dst=0)
+                dist.gather(send_f, recv_f, dst=0)
+        cfg3_step()
+        barrier()
+        e0c, e1c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps3 = 2
+        e0c.record()
+        for _ in range(reps3):
+            cfg3_step()
+        e1c.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0c.elapsed_time(e1c) / reps3], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms3 = float(t.item())
+        fb3 = int(plan3.workspace[8:12].view(torch.int32).item())
+        cfg3 = {"workload": f"configs[2]: the same {n3} problems at k={k3}, contiguous slices over {world} rank(s) (strong scaling)",
+                "ms_per_pass": ms3, "problems_per_s": n3 / (ms3 * 1e-3), "ranks": world,
+                "problems_on_rank0": hi3 - lo3, "exact_fallback_problems_rank0": fb3,
+                "gather": "weight tables + nFound to rank 0 (NCCL gather) inside the timed region; k-best lists stay on the owning rank" if world > 1 else "none (one rank)"}
+        del plan3, send_p, send_f, recv_p, recv_f
+        torch.cuda.empty_cache()
+
+    # ---- config 4 over the ranks: batched exact permanents n = 12..20 (dense U(0,1)), contiguous slices of every size
+    #      class per rank, results gathered on rank 0; and permanentProb weights of gated problems the same way
+    cfg4 = None
+    if not args.skip_config4:
+        per_n = 2000
+        plans4 = []
+        for nd_ in range(12, 21):
+            lo4, hi4 = per_n * rank // world, per_n * (rank + 1) // world
+            plans4.append(dev.PermanentPlan(synth.dense_square(hi4 - lo4, nd_, first=5000 * nd_ + lo4), nd_))
+        tot_local = sum(pl.n for pl in plans4)
+        send4 = torch.zeros(9 * (per_n // world + 1), dtype=torch.float64, device="cuda")
+        recv4 = [torch.empty_like(send4) for _ in range(world)] if rank == 0 else None
+        def cfg4_step():
+            o = 0
+            for pl in plans4:
+                pl.run()
+                send4[o:o + pl.n].copy_(pl.out); o += pl.n
+            if world > 1:
+                dist.gather(send4, recv4, dst=0)
+        cfg4_step()
+        barrier()
+        e0c, e1c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0c.record()
+        for _ in range(3):
+            cfg4_step()
+        e1c.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0c.elapsed_time(e1c) / 3], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms4 = float(t.item())
+        flops4 = sum(per_n * 3.0 * nd_ * 2.0 ** (nd_ - 1) for nd_ in range(12, 21))
+        # permanentProb (host call per rank on its slice of gated problems)
+        from probabilisticsemslam_b200 import api as _api
+        g2 = synth.g2_gated(1200, first=40000)
+        cond, _ = _api.condition_costs_batch(g2, device=local)
+        keep = [q for q in range(len(cond)) if cond.matrix(q).shape[0] - 1 <= 20]
+        lo5, hi5 = len(keep) * rank // world, len(keep) * (rank + 1) // world
+        sub = synth.pack([cond.matrix(q) for q in keep[lo5:hi5]], [int(cond.nL[q]) for q in keep[lo5:hi5]])
+        _api.permanent_prob_batch(sub, 1, device=local)
+        barrier()
+        t0 = time.perf_counter()
+        tabs, _st = _api.permanent_prob_batch(sub, 1, device=local)
+        flat = torch.from_numpy(np.concatenate([x.reshape(-1) for x in tabs])).cuda() if len(tabs) else torch.zeros(0, dtype=torch.float64, device="cuda")
+        if world > 1:
+            sz = torch.tensor([flat.numel()], dtype=torch.int64, device="cuda")
+            dist.all_reduce(sz, op=dist.ReduceOp.MAX)
+            pad = torch.zeros(int(sz.item()), dtype=torch.float64, device="cuda"); pad[:flat.numel()] = flat
+            dist.gather(pad, [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None, dst=0)
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cfg4 = {"workload": f"configs[3]: {per_n} dense matrices for each n = 12..20, contiguous slices over {world} rank(s); results gathered on rank 0",
+                "ms_per_pass": ms4, "matrices": 9 * per_n, "matrices_per_s": 9 * per_n / (ms4 * 1e-3),
+                "achieved_tflops": flops4 / (ms4 * 1e-3) / 1e12, "ranks": world, "matrices_on_rank0": tot_local,
+                "permanent_prob": {"problems": len(keep), "ms": 1e3 * float(t.item()),
+                                   "problems_per_s": len(keep) / float(t.item()),
+                                   "call": "pda_permanent_prob_batch_host on each rank's slice of gated problems (<= 21 rows), tables gathered on rank 0"}}
+        del plans4
+        torch.cuda.empty_cache()
 
     # ---- configs[0]: ONE 5x30 problem, k = 200, through the host call (the per-frame shape of the SLAM loop): the
     #      batch-of-one goes to the one-CTA-per-problem kernel; H2D, launch and D2H are inside the wall-clock time
@@ -361,19 +515,26 @@ def main():
                         "(the bytes below cross the bus inside the timed region, overlapped with computing); e2e can exceed "
                         "`value` because the device-resident pass additionally writes the 7 GB of k-best lists",
                 "matches_device_run": e2e_matches},
-        "gpu_launches": 2 * args.steps,  # per timed step: order_by_cost_kernel + murty_kernel<2>
+        # per timed step: order_by_cost_kernel + murty_kernel<2, true> (pruning) + murty_kernel<2, false> (exact, over the
+        # problems the pruning kernel handed back: none on this workload, the launch finds an empty list)
+        "gpu_launches": 3 * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                     "traffic": measured_traffic(n, k), "peak_source": pk_kind, "kernel": "murty_kernel<2>", "kernel_ms": kernel_ms,
+                     "traffic": measured_traffic(n, k), "peak_source": pk_kind, "kernel": "murty_kernel<2, true>", "kernel_ms": kernel_ms,
+                     "exact_fallback_problems": fallback_problems,
                      "algorithmic_bytes_per_launch": alg_bytes,
                      "note": "issue/ALU-pipe bound by construction (SURVEY.md 8d), not HBM bound. traffic (ncu, profiles/) exceeds the "
-                             "algorithmic bytes by the node arena: every Murty child (736 B of duals + pairing) is spilled once and half are "
-                             "read back (~445 KB per problem); inputs are read once"},
+                             "algorithmic bytes by the node arena: every KEPT Murty child (736 B of duals + pairing) is spilled once and the "
+                             "ones that reach the top are read back; children that cannot be among the k best are abandoned before they are stored; "
+                             "inputs are read once"},
         "extra": {"permanent_n24": {"gpu_ms": perm_ms, "unit": "ms", "flops": pplan.flops(),
                                     "achieved_tflops": pplan.flops() / (perm_ms * 1e-3) / 1e12,
                                     "fp64_peak_tflops_measured": fp64_peak},
                   "config0_single_5x30_k200": {"host_call_us_cta_kernel": lat.get("cta"), "host_call_us_warp_kernel": lat.get("warp"),
                                                "call": "assignmentProb, batch of one, host buffers (H2D + launch + D2H inside)"},
                   "moments_to_weights": mom,
+                  "config3_k1000_strong": cfg3,
+                  "permanent_batch_sharded": cfg4,
+                  "e2e_variants": e2e_variants,
                   "permanent_n28_sharded": {"ms": perm28_ms, "ranks": world, "value": perm28_value,
                                             "exchange": "all_gather of 16-byte (hi, lo) partials, summed in rank order" if world > 1 else "none",
                                             "achieved_tflops": 3.0 * 28 * 2.0 ** 27 / (perm28_ms * 1e-3) / 1e12}},
