@@ -329,10 +329,29 @@ def main():
             parts.copy_(rplan.partial)
     for _ in range(3):
         perm28_step()
+    # kernel + exchange as ONE CUDA graph: the collective is queued behind the kernel on the device, no Python and no
+    # launch latency between them (the exchange is 16 bytes: its cost is pure latency)
+    perm28_run, perm28_how = perm28_step, "stream launches"
+    if world > 1 and not os.environ.get("PDA_BENCH_NO_GRAPH"):
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                perm28_step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph28 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph28):
+                perm28_step()
+            perm28_run, perm28_how = graph28.replay, "one CUDA graph (kernel + NCCL all_gather)"
+        except Exception as exc:  # capture not possible here: plain launches
+            perm28_how = f"stream launches (graph capture failed: {type(exc).__name__})"
+    for _ in range(3):
+        perm28_run()
     barrier()
     e0.record()
     for _ in range(10):
-        perm28_step()
+        perm28_run()
     e1.record()
     torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1) / 10], dtype=torch.float64, device="cuda")
@@ -537,6 +556,7 @@ def main():
                   "e2e_variants": e2e_variants,
                   "permanent_n28_sharded": {"ms": perm28_ms, "ranks": world, "value": perm28_value,
                                             "exchange": "all_gather of 16-byte (hi, lo) partials, summed in rank order" if world > 1 else "none",
+                                            "launch": perm28_how,
                                             "achieved_tflops": 3.0 * 28 * 2.0 ** 27 / (perm28_ms * 1e-3) / 1e12}},
     }
     if world == 1 and not args.no_cpu:

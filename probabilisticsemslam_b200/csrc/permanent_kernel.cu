@@ -74,6 +74,12 @@ struct PermArgs {
     int maxN;           // largest dimension in the batch (sizes the shared-memory slots)
     dd* partial;        // [nMats * ctasPerMat]
     int dpBits;         // matrices whose SMALLER side is <= dpBits go to perm_dp_kernel instead (-1: none)
+    // fused finalisation: the CTA that finishes a matrix last sums the per-CTA partials (same fixed order as
+    // perm_finalize_kernel) and writes the result, so a large single matrix costs ONE launch
+    int fuse;
+    unsigned* done;     // [nMats] arrival counters (zero before the launch; the finishing CTA resets its counter)
+    double* out; int32_t* status; double* rangePartial;
+    int oneDim;         // > 0: a single oneDim x oneDim matrix at mats[0]; rows / cols / matOff are not read (range mode)
 };
 
 // Matrices with a small side are not walked by the NW kernel at all: see perm_dp_kernel.
@@ -333,6 +339,42 @@ __host__ __device__ constexpr int perm_min_blocks(int np) {
     return perm_cache0(np) ? (np <= 12 ? 4 : (np <= 16 ? 3 : 2)) : (np <= 16 ? 4 : (np <= 24 ? 3 : 2));
 }
 
+// Sums the per-CTA partials of matrix m (lane-strided, then a fixed shuffle tree: the order depends only on ctasPerMat,
+// so results are reproducible) and applies sign, factor 2 and the rectangular scale.  One warp.
+__device__ __forceinline__ void perm_finish_warp(const PermArgs& a, const int64_t m, double* __restrict__ out,
+                                                 int32_t* __restrict__ status, double* __restrict__ rangePartial, const int lane) {
+    dd t;
+    t.hi = 0.0;
+    t.lo = 0.0;
+    for (int c = lane; c < a.ctasPerMat; c += 32) {
+        const double2 v = __ldcg(reinterpret_cast<const double2*>(a.partial + (size_t)m * a.ctasPerMat + c));  // written by other CTAs
+        dd o;
+        o.hi = v.x; o.lo = v.y;
+        t = dd_add(t, o);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        dd other;
+        other.hi = __shfl_down_sync(FULL, t.hi, o);
+        other.lo = __shfl_down_sync(FULL, t.lo, o);
+        t = dd_add(t, other);
+    }
+    if (lane != 0) return;
+    if (a.rangeMode) {
+        rangePartial[0] = t.hi;
+        rangePartial[1] = t.lo;
+        return;
+    }
+    const int rows = a.oneDim > 0 ? a.oneDim : a.rows[m], cols = a.oneDim > 0 ? a.oneDim : a.cols[m];
+    const int n = rows > cols ? rows : cols;
+    if (n > PDA_MAX_PERM_DIM) { out[m] = 0.0; if (status) status[m] = 1; return; }  // nwPerm.cpp:327-330 throws
+    if (status) status[m] = 0;
+    if (n == 0) { out[m] = 1.0; return; }  // nwPerm.cpp:261-264
+    double p = (double)(4 * (n & 1) - 2) * (t.hi + t.lo);
+    if (rows != cols) p = p / kFactorial[rows > cols ? rows - cols : cols - rows];
+    out[m] = p;
+}
+
 template <int NP>
 __global__ void __launch_bounds__(PERM_THREADS, perm_min_blocks(NP)) perm_kernel(const PermArgs a) {
     extern __shared__ __align__(16) double smemD[];
@@ -346,11 +388,11 @@ __global__ void __launch_bounds__(PERM_THREADS, perm_min_blocks(NP)) perm_kernel
     double* sA = smemD + (size_t)slot * slotDoubles;
     double* sBase = sA + LD * a.maxN;
     const bool live = m < a.nMats;
-    const int rows = live ? a.rows[m] : 0, cols = live ? a.cols[m] : 0;
+    const int rows = live ? (a.oneDim > 0 ? a.oneDim : a.rows[m]) : 0, cols = live ? (a.oneDim > 0 ? a.oneDim : a.cols[m]) : 0;
     const int n = rows > cols ? rows : cols;
     const bool ok = live && n >= 1 && n <= NP && n <= PDA_MAX_PERM_DIM && n <= a.maxN && !perm_uses_dp(rows, cols, a.dpBits);
     if (ok) {
-        const double* A = a.mats + a.matOff[m];
+        const double* A = a.mats + (a.oneDim > 0 ? 0 : a.matOff[m]);
         // stage the matrix: ones outside the given block (nwPerm.cpp:226-228), zero rows beyond n
         for (int e = t; e < NP * n; e += tpm) {
             const int j = e % NP, k = e / NP;
@@ -405,6 +447,23 @@ __global__ void __launch_bounds__(PERM_THREADS, perm_min_blocks(NP)) perm_kernel
         dd tot = sWarp[w0];
         for (int w = 1; w < nw; ++w) tot = dd_add(tot, sWarp[w0 + w]);
         a.partial[(size_t)m * a.ctasPerMat + cta] = tot;
+    }
+    if (a.fuse) {  // the CTA that completes a matrix finalises it: no second launch
+        __shared__ int sLast[PERM_THREADS / 32];
+        if (live && t == 0) {
+            bool last = true;
+            if (a.ctasPerMat > 1) {
+                __threadfence();  // the partial above is visible before the arrival is counted
+                last = atomicAdd(&a.done[m], 1u) == (unsigned)a.ctasPerMat - 1u;
+            }
+            sLast[slot] = last ? 1 : 0;
+        }
+        __syncthreads();
+        if (live && t < 32 && sLast[slot] && !(a.dpBits >= 0 && perm_uses_dp(rows, cols, a.dpBits))) {
+            __threadfence();
+            perm_finish_warp(a, m, a.out, a.status, a.rangePartial, t);
+            if (t == 0 && a.ctasPerMat > 1) a.done[m] = 0u;  // ready for the next launch on this stream
+        }
     }
 }
 
@@ -462,37 +521,14 @@ __global__ void perm_finalize_kernel(const PermArgs a, double* __restrict__ out,
     const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (m >= a.nMats) return;
     if (a.dpBits >= 0 && !a.rangeMode) {
-        const int rows = a.rows[m], cols = a.cols[m];
+        const int rows = a.oneDim > 0 ? a.oneDim : a.rows[m], cols = a.oneDim > 0 ? a.oneDim : a.cols[m];
         if (perm_uses_dp(rows, cols, a.dpBits)) {  // the NW kernel skipped this one
             perm_dp_warp(a, m, rows, cols, smemD + (size_t)(threadIdx.x >> 5) * (2 * ((size_t)1 << a.dpBits) + 16), out, status, lane);
             return;
         }
     }
-    dd t;
-    t.hi = 0.0;
-    t.lo = 0.0;
-    for (int c = lane; c < a.ctasPerMat; c += 32) t = dd_add(t, a.partial[(size_t)m * a.ctasPerMat + c]);
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        dd other;
-        other.hi = __shfl_down_sync(FULL, t.hi, o);
-        other.lo = __shfl_down_sync(FULL, t.lo, o);
-        t = dd_add(t, other);
-    }
-    if (lane != 0) return;
-    if (a.rangeMode) {
-        rangePartial[0] = t.hi;
-        rangePartial[1] = t.lo;
-        return;
-    }
-    const int rows = a.rows[m], cols = a.cols[m];
-    const int n = rows > cols ? rows : cols;
-    if (n > PDA_MAX_PERM_DIM) { out[m] = 0.0; if (status) status[m] = 1; return; }  // nwPerm.cpp:327-330 throws
-    if (status) status[m] = 0;
-    if (n == 0) { out[m] = 1.0; return; }  // nwPerm.cpp:261-264
-    double p = (double)(4 * (n & 1) - 2) * (t.hi + t.lo);
-    if (rows != cols) p = p / kFactorial[rows > cols ? rows - cols : cols - rows];
-    out[m] = p;
+    if (a.fuse) return;  // perm_kernel finalised this one itself
+    perm_finish_warp(a, m, out, status, rangePartial, lane);
 }
 
 template <int NP>
@@ -564,18 +600,24 @@ int launch_permanent_batch(const double* mats, const int64_t* matOff, const int3
     const size_t dpSmem = noneDp ? 0 : (size_t)4 * (2 * ((size_t)1 << dpBits) + 16) * sizeof(double);  // 4 warps per finalize CTA
     if (dpSmem > 48 * 1024) PDA_CUDA_TRY(cudaFuncSetAttribute(perm_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dpSmem));
     if (allDp) {
-        PermArgs d = {mats, matOff, rows, cols, nMats, 0, 0, 0, 1, 32, 0, effDim, nullptr, dpBits};
+        PermArgs d = {mats, matOff, rows, cols, nMats, 0, 0, 0, 1, 32, 0, effDim, nullptr, dpBits, 0, nullptr, nullptr, nullptr, nullptr, 0};
         perm_finalize_kernel<<<(unsigned)((nMats + 3) / 4), 128, dpSmem, stream>>>(d, out, status, nullptr);
         PDA_CUDA_TRY(cudaGetLastError());
         return PDA_OK;
     }
+    // workspace: arrival counters of the fused finalisation, then the per-CTA partial sums
+    const int64_t cntBytes = (nMats * 4 + 15) / 16 * 16;
+    const int64_t partBytes = workspaceBytes - cntBytes;
     PermShape sh = perm_shape(nMats, effDim, dev.smCount, 0);
-    while (sh.ctasPerMat > 1 && (int64_t)sh.ctasPerMat * nMats * (int64_t)sizeof(dd) > workspaceBytes) sh.ctasPerMat >>= 1;
-    if ((int64_t)sh.ctasPerMat * nMats * (int64_t)sizeof(dd) > workspaceBytes)
+    while (sh.ctasPerMat > 1 && (int64_t)sh.ctasPerMat * nMats * (int64_t)sizeof(dd) > partBytes) sh.ctasPerMat >>= 1;
+    if ((int64_t)sh.ctasPerMat * nMats * (int64_t)sizeof(dd) > partBytes)
         return fail(PDA_ERR_WORKSPACE, "permanent: workspace of %lld B too small (need %lld)", (long long)workspaceBytes,
-                    (long long)(nMats * (int64_t)sizeof(dd)));
+                    (long long)(cntBytes + nMats * (int64_t)sizeof(dd)));
+    unsigned* done = reinterpret_cast<unsigned*>(workspace);
+    if (sh.ctasPerMat > 1) PDA_CUDA_TRY(cudaMemsetAsync(done, 0, (size_t)nMats * 4, stream));
     PermArgs a = {mats, matOff, rows, cols, nMats, 0, 0, 0, sh.chunk, sh.threadsPerMat, sh.ctasPerMat, effDim,
-                  reinterpret_cast<dd*>(workspace), noneDp ? -1 : dpBits};
+                  reinterpret_cast<dd*>(reinterpret_cast<unsigned char*>(workspace) + cntBytes), noneDp ? -1 : dpBits,
+                  1, done, out, status, nullptr, 0};
     // blockIdx.y is limited to 65535: slice the batch
     const int64_t slots = PERM_THREADS / sh.threadsPerMat, perLaunch = 65535 * slots;
     for (int64_t m0 = 0; m0 < nMats; m0 += perLaunch) {
@@ -583,10 +625,15 @@ int launch_permanent_batch(const double* mats, const int64_t* matOff, const int3
         s.matOff = matOff + m0; s.rows = rows + m0; s.cols = cols + m0;
         s.nMats = std::min<int64_t>(perLaunch, nMats - m0);
         s.partial = a.partial + m0 * sh.ctasPerMat;
+        s.done = done + m0;
+        s.out = out + m0;
+        s.status = status ? status + m0 : nullptr;
         PDA_TRY(dispatch(s, stream));
     }
-    perm_finalize_kernel<<<(unsigned)((nMats + 3) / 4), 128, dpSmem, stream>>>(a, out, status, nullptr);
-    PDA_CUDA_TRY(cudaGetLastError());
+    if (!noneDp) {  // only the short-sided matrices are left for this kernel: everything else finalised itself
+        perm_finalize_kernel<<<(unsigned)((nMats + 3) / 4), 128, dpSmem, stream>>>(a, out, status, nullptr);
+        PDA_CUDA_TRY(cudaGetLastError());
+    }
     return PDA_OK;
 }
 
@@ -601,19 +648,14 @@ int launch_permanent_range(const double* A, int32_t n, uint64_t begin, uint64_t 
         sh.ctasPerMat = (int)std::max<int64_t>(1, (workspaceBytes - 64) / (int64_t)sizeof(dd));
         if (workspaceBytes < 64 + (int64_t)sizeof(dd)) return fail(PDA_ERR_WORKSPACE, "permanent_range: workspace too small");
     }
-    // the single matrix is described by tiny device-side descriptors at the head of the workspace
+    // one launch: the matrix is described in the kernel arguments (oneDim), the CTA that arrives last adds the per-CTA
+    // partials up; the arrival counter at the head of the workspace is zeroed by a memset node in front of the kernel
     unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
-    int64_t* dOff = reinterpret_cast<int64_t*>(ws);
-    int32_t* dRows = reinterpret_cast<int32_t*>(ws + 8);
-    int32_t* dCols = reinterpret_cast<int32_t*>(ws + 12);
-    struct { int64_t off; int32_t r, c; } desc = {0, n, n};
-    PDA_CUDA_TRY(cudaMemcpyAsync(ws, &desc, 16, cudaMemcpyHostToDevice, stream));
-    PermArgs a = {A, dOff, dRows, dCols, 1, begin, end, 1, sh.chunk, sh.threadsPerMat, sh.ctasPerMat, n,
-                  reinterpret_cast<dd*>(ws + 64), -1};
-    PDA_TRY(dispatch(a, stream));
-    perm_finalize_kernel<<<1, 32, 0, stream>>>(a, nullptr, nullptr, partial);
-    PDA_CUDA_TRY(cudaGetLastError());
-    return PDA_OK;
+    unsigned* done = reinterpret_cast<unsigned*>(ws);
+    if (sh.ctasPerMat > 1) PDA_CUDA_TRY(cudaMemsetAsync(done, 0, 4, stream));
+    PermArgs a = {A, nullptr, nullptr, nullptr, 1, begin, end, 1, sh.chunk, sh.threadsPerMat, sh.ctasPerMat, n,
+                  reinterpret_cast<dd*>(ws + 64), -1, 1, done, nullptr, nullptr, partial, n};
+    return dispatch(a, stream);
 }
 
 }  // namespace pda
@@ -623,7 +665,8 @@ using namespace pda;
 extern "C" {
 
 int64_t pda_permanent_workspace_bytes(int64_t nMats) {
-    return 64 + 16 * (std::max<int64_t>(nMats, 1) + 8192);
+    const int64_t n = std::max<int64_t>(nMats, 1);
+    return 64 + 16 * (n + 8192) + (n * 4 + 15) / 16 * 16;  // per-CTA partials + arrival counters
 }
 
 int pda_permanent_batch(const double* mats, const int64_t* matOff, const int32_t* rows, const int32_t* cols,
@@ -633,8 +676,11 @@ int pda_permanent_batch(const double* mats, const int64_t* matOff, const int32_t
     if (nMats == 0) return PDA_OK;
     if (!mats || !matOff || !rows || !cols || !out || !workspace) return fail(PDA_ERR_INVALID, "permanent: NULL argument");
     if (maxDim < 0) return fail(PDA_ERR_INVALID, "permanent: maxDim < 0");
+    // the dimensions live on the device, so this entry cannot tell whether any matrix has a short side: it walks every
+    // matrix the reference's way (NW on the ones-padded square).  The *_host entries, which see the dimensions, send
+    // short-sided matrices to the cancellation-free subset programme (perm_dp_warp).
     return launch_permanent_batch(mats, matOff, rows, cols, nMats, maxDim, out, status, workspace, workspaceBytes,
-                                  reinterpret_cast<cudaStream_t>(stream));
+                                  reinterpret_cast<cudaStream_t>(stream), -1, PDA_MAX_DIM + 1);
 }
 
 int pda_permanent_batch_host(const double* mats, const int64_t* matOff, const int32_t* rows, const int32_t* cols,
