@@ -329,10 +329,12 @@ def main():
             parts.copy_(rplan.partial)
     for _ in range(3):
         perm28_step()
-    # kernel + exchange as ONE CUDA graph: the collective is queued behind the kernel on the device, no Python and no
-    # launch latency between them (the exchange is 16 bytes: its cost is pure latency)
+    # Optional (PDA_BENCH_GRAPH=1): kernel + exchange as ONE CUDA graph, so the collective is queued behind the kernel on
+    # the device with no Python and no launch latency between them.  OFF by default: an 8-rank run with the capture
+    # enabled did not come back within its time limit in round 2 and could not be re-examined, so the measured path
+    # stays the plain stream launches that every earlier run used.
     perm28_run, perm28_how = perm28_step, "stream launches"
-    if world > 1 and not os.environ.get("PDA_BENCH_NO_GRAPH"):
+    if world > 1 and os.environ.get("PDA_BENCH_GRAPH") == "1":
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
