@@ -47,12 +47,13 @@ WORKLOAD = "configs[1]: 100k KITTI-shaped problems (3-8 detections x 30 landmark
 
 
 def measured_traffic(n, k):
-    """DRAM bytes of one launch of the headline kernel from the committed ncu capture (profiles/traffic.json),
-    when it was taken at this problem count; None otherwise."""
+    """DRAM bytes of one launch of the headline kernel from the committed ncu capture (profiles/traffic.json).  The
+    capture was taken over fewer problems than a bench launch (ncu replays the kernel ~40 times); problems are
+    independent and alike, so the per-problem figure is scaled to this launch's problem count.  None at another k."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             t = json.load(f)["murty_kernel<2, true>"]
-        return t["dram_bytes"] if (t["problems"] == n and t["k"] == k) else None
+        return int(t["bytes_per_problem"] * n) if t["k"] == k else None
     except (OSError, KeyError, ValueError):
         return None
 
@@ -542,6 +543,7 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
                      "traffic": measured_traffic(n, k), "peak_source": pk_kind, "kernel": "murty_kernel<2, true>", "kernel_ms": kernel_ms,
                      "exact_fallback_problems": fallback_problems,
+                     "traffic_source": "profiles/traffic.json: ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch over 20 000 problems, scaled per problem",
                      "algorithmic_bytes_per_launch": alg_bytes,
                      "note": "issue/ALU-pipe bound by construction (SURVEY.md 8d), not HBM bound. traffic (ncu, profiles/) exceeds the "
                              "algorithmic bytes by the node arena: every KEPT Murty child (736 B of duals + pairing) is spilled once and the "

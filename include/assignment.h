@@ -65,6 +65,15 @@ inline std::vector<double> computeQuadricCostMatrix(const std::vector<Eigen::Mat
     for (size_t i = 0; i < cov2.size(); i++) for (int j = 0; j < 9; j++) d[9 * i + j] = cov2[i].data()[j];
     return computeQuadricCostMatrixRaw(a, b, c, d, nonassign);
 }
+/* ... and the reference's exact signature (assignment.h:31-32): the last argument is its `const semConsts& runConsts`, of
+ * which only NONASSIGN_QUADRIC is read (assignment.cpp:718).  A template, so this header does not need constsUtils.h. */
+template <class Consts>
+inline std::vector<double> computeQuadricCostMatrix(const std::vector<Eigen::Matrix<double, 3, 1> >& m1,
+                                                    const std::vector<Eigen::Matrix<double, 3, 3> >& cov1,
+                                                    const std::vector<Eigen::Vector3d>& m2,
+                                                    const std::vector<Eigen::Matrix<double, 3, 3> >& cov2, const Consts& runConsts) {
+    return computeQuadricCostMatrix(m1, cov1, m2, cov2, (double)runConsts.NONASSIGN_QUADRIC);
+}
 #endif
 
 /* asgnBB (reference assignment.h:21, assignment.cpp:724-775) on raw boxes: five doubles per box

@@ -67,7 +67,10 @@ double pda_diag_dfma_tflops(void);
  *   row4colBest         problem p, hypothesis i at row4colBest + r4cOff[p] + i*numCol[p]   (may be NULL)
  *   col4rowBest         problem p, hypothesis i at col4rowBest + c4rOff[p] + i*numRow[p]   (may be NULL)
  *   gainBest            problem p, hypothesis i at gainBest[p*k + i]                       (may be NULL)
- *   nFound[p]           number of hypotheses found, 0 = infeasible (the reference's return value)
+ *   nFound[p]           number of hypotheses found, 0 = infeasible (the reference's return value); -1 = the problem was
+ *                       not solved because its dimensions are malformed (numCol < 1, numCol > numRow, nL + numCol !=
+ *                       numRow with weights) or exceed maxNumRow / maxNumCol of this call -- only reachable through the
+ *                       device-pointer entry, the *_host entries reject such batches up front
  *   probs, probOff, nL  weightMode != 0: numCol[p] x (nL[p]+1) row-major table at probs + probOff[p]
  *   workspace           >= pda_murty_workspace_bytes(...) gives full occupancy; smaller is legal
  *                       (fewer problems in flight) down to one problem's worth

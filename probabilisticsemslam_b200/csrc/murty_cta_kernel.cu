@@ -529,8 +529,9 @@ __device__ void solve_problem_cta(const MurtyArgs& a, const CtaGeometry& cg, con
     const int n = a.numRow[p], nc = a.numCol[p];
     const bool wantW = a.weightMode != PDA_WEIGHTS_NONE;
     const int nL = wantW ? a.nL[p] : 0;
-    if (nc < 1 || nc > n || n > 32 * R || nc > PDA_CTA_MAX_COL || (wantW && nL + nc != n)) {
-        if (threadIdx.x == 0) a.nFound[p] = 0;
+    if (nc < 1 || nc > n || n > 32 * R || nc > PDA_CTA_MAX_COL || n > a.geo.nodeDim || n * nc > a.geo.cCap || nc > a.geo.maxCol ||
+        (wantW && nL + nc != n)) {
+        if (threadIdx.x == 0) a.nFound[p] = -1;  // malformed or beyond the launch's maxima: not solved (0 would mean infeasible)
         return;
     }
     const WarpSmem sm = warp_view(S, cg, R, warp);

@@ -56,8 +56,10 @@ __device__ void solve_problem(const MurtyArgs& a, const long long p, const WarpS
     const int D = a.geo.nodeDim;
     const bool wantW = a.weightMode != PDA_WEIGHTS_NONE;
     const int nL = wantW ? a.nL[p] : 0;
-    if (nc < 1 || nc > n || n > 32 * R || (wantW && nL + nc != n)) {
-        if (lane == 0) a.nFound[p] = 0;
+    // malformed, or larger than the maxima this launch was sized for (shared-memory matrix, node slots, arena): not
+    // solved; reported as -1, which no reference call can return (0 = infeasible)
+    if (nc < 1 || nc > n || n > 32 * R || n > a.geo.nodeDim || n * nc > a.geo.cCap || nc > a.geo.maxCol || (wantW && nL + nc != n)) {
+        if (lane == 0) a.nFound[p] = -1;
         return;
     }
     const double* Cg = a.costs + a.costOff[p];
@@ -349,7 +351,7 @@ __global__ void lap_kernel(const LapArgs a, const int smemPerWarp, const int cCa
     const WarpSmem sm = carve<R>(smemRaw + (size_t)warp * smemPerWarp, g);
     const int n = a.numRow[p], nc = a.numCol[p];
     const int ncGain = a.numCol4Gain ? a.numCol4Gain[p] : nc;
-    if (nc < 0 || nc > n || n > 32 * R) { if (lane == 0 && a.feasible) a.feasible[p] = 0; return; }
+    if (nc < 0 || nc > n || n > 32 * R || n * nc > cCap) { if (lane == 0 && a.feasible) a.feasible[p] = 0; return; }  // malformed or beyond the declared maxima
     double CDelta = stage_safe_matrix(a.costs + a.costOff[p], sm.C, n * nc, a.maximize != 0, a.makeSafe != 0, lane);
     CDelta = CDelta * (double)nc;
     Node<R> nd;
@@ -427,6 +429,7 @@ int murty_geometry(int32_t k, int32_t maxNumRow, int32_t maxNumCol, bool weights
         return fail(PDA_ERR_UNSUPPORTED, "murty: numRow %d exceeds PDA_MAX_DIM %d", maxNumRow, PDA_MAX_DIM);
     g->R = (maxNumRow + 31) / 32;
     if (g->R == 3) g->R = 4;
+    g->maxCol = maxNumCol;
     const int D = 32 * g->R;
     g->nodeDim = round_up(maxNumRow, 8);
     g->nodeStride = round_up(18 * g->nodeDim + 4 * (g->R + 1), 16);

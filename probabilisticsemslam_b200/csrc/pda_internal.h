@@ -29,6 +29,7 @@ int current_device_info(DeviceInfo* out);
 // ---- Murty k-best (murty_kernel.cu) ----------------------------------------------------------
 struct MurtyGeometry {
     int R;              // row slots per lane: numRow <= 32*R
+    int maxCol;         // largest numCol the node slots were counted for
     int nodeDim;        // padded per-node array length
     int nodeStride;     // bytes per stored node
     int maxNodes;       // node slots per warp arena

@@ -35,8 +35,35 @@ def test_shim_library_exports_the_reference_entry_points():
     for sym in ["kBest2D(", "kBest2DCutoff(", "assign2D(", "shortestPathCPP(", "assignmentProb(", "permanentProb(",
                 "bruteForceProb(", "conditionCosts(", "toProbs(", "conditionedPermanentRaw(", "permanentExactRaw(",
                 "permanentApproximationRaw(", "computeQuadricCostMatrixRaw(", "getAssignmentProbsFromMoments(",
-                "getAssignmentProbsFromCosts(", "asgnBBRaw(", "assignmentProbBatch("]:
+                "getAssignmentProbsFromCosts(", "asgnBBRaw(", "assignmentProbBatch(", "permanentProbBatch(",
+                "permanentExactShardedRaw(", "permanentExactLongRaw("]:
         assert sym in out, f"{sym} missing from the C++ drop-in layer"
+
+
+def test_reference_typed_overloads_compile():
+    """include/nwPerm.h and include/assignment.h with PDA_HAVE_EIGEN on (a stand-in <Eigen/Core>): the overloads that carry
+    the reference's own argument types are at least type-checked on every CPU run (they RUN in tests/test_gpu_dropin.py)."""
+    import subprocess
+    src = os.path.join(ROOT, "tests", "cpp", "eigen_overloads_driver.cpp")
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I", os.path.join(ROOT, "tests", "cpp", "eigen_stub"),
+                        "-I", os.path.join(ROOT, "include"), src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-800:]
+
+
+def test_multi_device_entry_points_fail_loudly_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from probabilisticsemslam_b200 import _lib
+    lib = _lib.lib()
+    dev = (ctypes.c_int32 * 2)(0, 1)
+    A = (ctypes.c_double * 4)(1, 2, 3, 4)
+    out = (ctypes.c_double * 1)()
+    assert lib.pda_permanent_sharded_host(A, 2, dev, 2, out) == -2 and b"no CUDA device" in lib.pda_last_error()
+    assert lib.pda_permanent_sharded_host(A, 2, None, 0, out) == -1
+    assert lib.pda_murty_batch_host_multi(None, None, None, None, 5, 10, 1, 42.0, 0, 0, None, None, None, None, None, None,
+                                          0, None, None, None, dev, 2) == -1
+    assert lib.pda_host_alloc(1024) is None      # page-locked memory needs a device too
 
 
 def test_no_cpu_fallback():
@@ -56,7 +83,8 @@ def test_host_side_knobs_work_without_a_device():
     from probabilisticsemslam_b200 import _lib
     lib = _lib.lib()
     prev = lib.pda_murty_set_path(2)
-    assert prev in (0, 1, 2) and lib.pda_murty_set_path(prev) == 2
+    assert prev in (0, 1, 2, 3) and lib.pda_murty_set_path(prev) == 2
+    assert lib.pda_murty_set_path(3) == prev and lib.pda_murty_set_path(prev) == 3   # the pruning kernel can be pinned
     assert lib.pda_murty_set_path(7) == -1 and b"path" in lib.pda_last_error()
     lib.pda_set_approx_seed(123)
     lib.pda_set_approx_seed(20260217)

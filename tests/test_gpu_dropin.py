@@ -108,3 +108,49 @@ def test_moments_and_approximation_through_the_cpp_headers(gpu_api, oracle):
     np.testing.assert_array_equal(probs, gpu_api.getAssignmentProbs(lm, lc, mm, mc, 10.0, 200))
     np.testing.assert_allclose(probs, oracle.association_from_moments(lm, lc, mm, mc, 10.0, 200), rtol=1e-9, atol=1e-300)
     assert abs(float(lines["approx"][1]) / 720.0 - 1.0) < 0.2     # 300 trials, ~68 % accepted: 4 % standard error
+
+
+def test_reference_typed_overloads(gpu_api, oracle):
+    """The overloads that take the reference's own argument types (const Eigen::MatrixXd&, std::vector<Eigen::Vector3d>,
+    const semConsts&) -- compiled against tests/cpp/eigen_stub because Eigen is not installed -- give the numbers of the
+    raw forms: permanentExact / Square / Long (nwPerm.h:22-25), conditionedPermanent (assignment.h), the sharded
+    permanent, and computeQuadricCostMatrix with runConsts (assignment.h:31-32)."""
+    exe = os.path.join(ROOT, "tests", "cpp", "build", "eigen_overloads_b200")
+    assert os.path.exists(exe), "tests/cpp/build/eigen_overloads_b200 missing: run __graft_entry__.build()"
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stderr[-500:]
+    out = {ln.split()[0]: ln.split()[1:] for ln in run.stdout.splitlines() if ln.strip()}
+    A = np.array([[0.25 + 0.5 * ((7 * i + 3 * j) % 5) for j in range(5)] for i in range(5)])
+    B = np.array([[1.0 + 0.125 * ((5 * i + 2 * j) % 7) for j in range(5)] for i in range(3)])
+    wantA = oracle.permanent_exact_square(A)[0]
+    from truth import perm_injective
+    wantB = perm_injective(B)
+    for tag in ("permanentExact", "permanentExactSquare", "permanentExactLong", "permanentExactSharded"):
+        np.testing.assert_allclose(float(out[tag][0]), wantA, rtol=1e-12)
+    for tag in ("permanentExactRect", "permanentExactLongRect", "conditionedPermanent", "conditionedPermanentLong"):
+        np.testing.assert_allclose(float(out[tag][0]), wantB, rtol=1e-12)
+    assert out["throwsAbove32"] == ["1"] and out["quadricCostsSame"] == ["1"]
+    lm = np.array([[2.0 * i + 0.3 * d for d in range(3)] for i in range(4)])
+    lc = np.zeros((4, 3, 3))
+    for i in range(4):
+        lc[i] = np.diag([0.5 + 0.1 * i + 0.05 * d for d in range(3)]); lc[i][0, 1] = lc[i][1, 0] = 0.02
+    mm = np.array([[2.0 * i + 0.4 + 0.2 * d for d in range(3)] for i in range(2)])
+    mc = np.zeros((2, 3, 3))
+    for i in range(2):
+        mc[i] = np.diag([0.4 + 0.07 * d for d in range(3)]); mc[i][1, 2] = mc[i][2, 1] = -0.03
+    want = gpu_api.computeQuadricCostMatrix(lm, lc, mm, mc, 10.0)
+    got = np.array([float(x) for x in out["quadricCosts"]]).reshape(want.shape, order="F")
+    np.testing.assert_array_equal(got.view(np.int64), want.view(np.int64))
+
+
+def test_permanent_exact_long(gpu_api, oracle):
+    """permanentExactLong (nwPerm.cpp:386-400): the reference runs the same double kernel and only divides in long
+    double, so the double result must agree to 1e-9 (observed: to the last bits) for square and rectangular input."""
+    for n in (1, 4, 9, 14):
+        A = synth.dense_square(1, n, first=600 + n)[0].reshape(n, n, order="F")
+        np.testing.assert_allclose(gpu_api.permanentExactLong(A), oracle.permanent_exact_square(A)[0], rtol=1e-9)
+    from truth import perm_injective
+    R = synth.dense_square(1, 6, first=77)[0].reshape(6, 6, order="F")[:4, :]
+    np.testing.assert_allclose(gpu_api.permanentExactLong(R), perm_injective(R), rtol=1e-9)
+    with pytest.raises(RuntimeError):
+        gpu_api.permanentExactLong(np.ones((33, 33)))

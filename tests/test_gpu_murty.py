@@ -333,3 +333,28 @@ def test_full_size_every_hypothesis_vs_reference(gpu_api, oracle):
         valid = (np.arange(k)[None, :] < want["n_found"][:, None]).reshape(-1)
         assert not np.any((got.gain.reshape(-1).view(np.int64) != want["gain"].view(np.int64)) & valid), "gain bits differ"
         np.testing.assert_allclose(got.probs, want["probs"], rtol=1e-9, atol=0)
+
+
+def test_malformed_problem_is_reported_not_solved(gpu_api):
+    """Device-pointer entry: a problem whose dimensions are malformed, or larger than the maxima the call declared, is
+    reported as nFound = -1 (0 would mean "infeasible") and does not disturb its neighbours."""
+    import torch
+    from probabilisticsemslam_b200 import device as dev
+    pb = synth.g1_dense(6, first=4321)
+    good = dev.MurtyPlan(pb, k=10, weights=True)
+    good.run()
+    torch.cuda.synchronize()
+    want = good.n_found.cpu().numpy().copy()
+    want_probs = good.probs.cpu().numpy().copy()
+    bad = dev.MurtyPlan(pb, k=10, weights=True)
+    bad.num_col[2] = 0                                   # no detections
+    bad.num_row[4] = int(bad.max_row) + 3                # more rows than the launch was sized for
+    bad.run()
+    torch.cuda.synchronize()
+    got = bad.n_found.cpu().numpy()
+    assert got[2] == -1 and got[4] == -1
+    keep = [0, 1, 3, 5]
+    assert np.array_equal(got[keep], want[keep])
+    for p in keep:
+        o, sz = int(good.prob_off_h[p]), int(pb.nM[p]) * (int(pb.nL[p]) + 1)
+        assert np.array_equal(bad.probs.cpu().numpy()[o:o + sz], want_probs[o:o + sz])
