@@ -6,6 +6,7 @@
 #include "pda_internal.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -33,11 +34,15 @@ class DeviceScope {
 public:
     DeviceScope() : dev_(-1), prev_(-1), fails_(0) {}
     int enter(int device) {
-        int n = 0;
-        cudaError_t e = cudaGetDeviceCount(&n);
-        if (e != cudaSuccess || n == 0) {
-            (void)cudaGetLastError();
-            return fail(PDA_ERR_CUDA, "no CUDA device available (libpda_b200 has no CPU fallback)");
+        static std::atomic<int> known(0);  // the device count does not change while the process lives
+        int n = known.load(std::memory_order_relaxed);
+        if (n == 0) {
+            cudaError_t e = cudaGetDeviceCount(&n);
+            if (e != cudaSuccess || n == 0) {
+                (void)cudaGetLastError();
+                return fail(PDA_ERR_CUDA, "no CUDA device available (libpda_b200 has no CPU fallback)");
+            }
+            known.store(n, std::memory_order_relaxed);
         }
         if (device < 0 || device >= n || device >= PDA_MAX_DEVICES) return fail(PDA_ERR_INVALID, "device %d out of range (have %d)", device, n);
         if (cudaGetDevice(&prev_) != cudaSuccess) { (void)cudaGetLastError(); prev_ = -1; }
