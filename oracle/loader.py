@@ -48,6 +48,7 @@ class CpuChecker:
         f("asgn_bb", None, [_ptr, C.c_long, _ptr, C.c_long, _dbl, _ptr])
         if prefix == "orc":  # restatement only: needs Eigen on the reference side (oracle_quadric.c)
             f("permanent_approx", _dbl, [_ptr, _i64, _i64, _i64, C.c_uint64, _i64, _ptr])
+            f("kbest2d_cutoff_pruned", _i64, [_i64, _i64, _i64, _int, _ptr, _ptr, _ptr, _ptr, _dbl, _i64, _ptr])
             f("quadric_covs", None, [_ptr, _i64, _ptr])
             f("quadric_cost_matrix", None, [_ptr, _ptr, _i64, _ptr, _ptr, _i64, _dbl, _ptr])
             f("association_from_moments", _int, [_ptr, _ptr, _i64, _ptr, _ptr, _i64, _dbl, _i64, _ptr])
@@ -73,6 +74,15 @@ class CpuChecker:
 
     def kbest2d_cutoff(self, k, cmat, cutoff=42.0, maximize=False):
         return self._kbest("_kbest2d_cutoff", k, cmat, maximize, float(cutoff))
+
+    def kbest2d_cutoff_pruned(self, k, cmat, cutoff=42.0, maximize=False, max_col=None):
+        """CPU model of the CUDA pruning kernel's decisions (oracle_murty.c): (n or -2 if the kernel would fall back to the
+        exact kernel, row4col, col4row, gains, stats{children, abandoned, dropped_done, kept, tightenings, slots})."""
+        stats = np.zeros(6, np.int64)
+        mc = int(np.asarray(cmat).shape[1] if max_col is None else max_col)
+        n, r4c, c4r, g = self._kbest("_kbest2d_cutoff_pruned", k, cmat, maximize, float(cutoff), mc, _p(stats))
+        names = ["children", "abandoned", "dropped_done", "kept", "tightenings", "slots_at_tightening"]
+        return n, r4c, c4r, g, dict(zip(names, (int(x) for x in stats)))
 
     def kbest2d_after_cutoff(self, k, cmat, maximize, first_cmat, first_maximize, first_cutoff):
         first = np.ascontiguousarray(np.asfortranarray(first_cmat, dtype=np.float64).reshape(-1, order="F"))

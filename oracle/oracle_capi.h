@@ -35,6 +35,13 @@ int64_t orc_kbest2d_cutoff(int64_t k, int64_t numRow, int64_t numCol, int maximi
 int64_t orc_kbest2d_after_cutoff(int64_t k, int64_t numRow, int64_t numCol, int maximize, const double* C,
                                  int64_t* col4row, int64_t* row4col, double* gain,
                                  int firstMaximize, const double* firstC, double firstCutoff);
+/* CPU model of the CUDA pruning kernel's decisions (bound, tightening, abandonment, tie bail-out) over the reference
+ * arithmetic: returns what kBest2DCutoff returns, or -2 where the kernel would hand the problem to the exact kernel.
+ * maxCol = the batch's largest numCol (sizes the open list like the kernel's geometry).  stats[6]: children, abandoned,
+ * dropped when finished, kept, tightenings, slots at tightening.  No `ref_` twin: it models THIS repository's kernel. */
+int64_t orc_kbest2d_cutoff_pruned(int64_t k, int64_t numRow, int64_t numCol, int maximize, const double* C,
+                                  int64_t* col4row, int64_t* row4col, double* gain, double cutoff,
+                                  int64_t maxCol, int64_t* stats);
 /* shortestPathCPP.cpp:735-762.  Returns 1 solved / 0 infeasible. */
 int orc_assign2d(int64_t numRow, int64_t numCol, int maximize, const double* C,
                  int64_t* col4row, int64_t* row4col, double* u, double* v, double* gain);

@@ -56,6 +56,9 @@ typedef struct { HeapItem* a; int64_t len, cap; } Heap;
 typedef struct { int toCut; int maximize; double cutoffGain; } CutState;
 
 static _Thread_local int64_t g_pops, g_children, g_iters, g_evals, g_maxHeap;
+/* search-distance limit of the pruning model below (INFINITY = the plain reference behaviour) */
+static _Thread_local double t_limit = INFINITY;
+static _Thread_local int t_limit_hit = 0;
 
 static Node* node_new(int64_t n) {
     Node* s = (Node*)malloc(sizeof(Node));
@@ -142,6 +145,7 @@ static int dijkstra_augment(Node* s, const double* C, int64_t n, int64_t startCo
     const double INF = INFINITY;
     int64_t nScannedCols = 0, cur = startCol, sink = -1;
     double delta = 0;
+    t_limit_hit = 0;
     for (int64_t r = 0; r < n; r++) { w->scanned[r] = 0; w->spc[r] = INF; }
 
     do {
@@ -161,6 +165,7 @@ static int dijkstra_augment(Node* s, const double* C, int64_t n, int64_t startCo
         w->scanned[best] = 1;
         w->inScan[best] = 0;
         delta = w->spc[best];
+        if (delta > t_limit) { t_limit_hit = 1; return 2; }  /* pruning model only: this child cannot be among the hypotheses still wanted */
         if (s->col4row[best] == -1) sink = best; else cur = s->col4row[best];
     } while (sink == -1);
 
@@ -394,6 +399,123 @@ int orc_shortest_path(int64_t numRow, int64_t numCol, int64_t numCol4Gain, const
     node_free(s);
     work_free(&w);
     return infeasible;
+}
+
+/* ---- CPU model of the pruning kernel (murty_kernel<R, true>, probabilisticsemslam_b200/csrc/murty_kernel.cu) -------
+ * TEST INFRASTRUCTURE: restates the DECISIONS of the CUDA fast path -- the bound T, when and how it is tightened, which
+ * children are abandoned or dropped, when a selection counts as tied -- on top of this file's reference arithmetic, so the
+ * soundness of those rules can be checked on the CPU against the plain enumeration above (tests/test_pruning_model.py) and
+ * its counters against the kernel's (-DPDA_FAST_STATS).  Same constants, same operand order as the kernel:
+ *   cap    = roundup32(k + 2*maxCol + 8 + 32) slots; a split that might overflow them bails
+ *   m      = k - sweep hypotheses still wanted; tighten when (T == inf ? live >= m : live - m >= trig); trig = live - m + 8
+ *   limit  = (T - gain(parent)) + 1e-7 * (T + 1)     a search is abandoned once its distance exceeds it
+ *   tie    = a second live entry with the winner's gain bits  =>  bail (the exact kernel redoes the problem)
+ * Returns the number of hypotheses, or -2 if the model bails.  stats[6]: children, abandoned, dropped when finished,
+ * kept, tightenings, slots at tightening. */
+typedef struct { double gain; Node* node; int live; } Slot;
+
+static void model_tighten(Slot* q, int64_t* len, int64_t* live, double* T, int64_t m) {
+    double lo = INFINITY, hi = -INFINITY;
+    for (int64_t i = 0; i < *len; i++) if (q[i].live) { if (q[i].gain < lo) lo = q[i].gain; if (q[i].gain > hi) hi = q[i].gain; }
+    double Tn = hi;
+    if (hi > lo) {
+        const double width = (hi - lo) * 0.03125;
+        const double inv = 1.0 / width;
+        int64_t hist[32] = {0};
+        for (int64_t i = 0; i < *len; i++) if (q[i].live) {
+            int b = (int)((q[i].gain - lo) * inv);
+            b = b > 31 ? 31 : (b < 0 ? 0 : b);
+            hist[b]++;
+        }
+        int64_t cum = 0; int bstar = -1;
+        for (int b = 0; b < 32; b++) { cum += hist[b]; if (cum >= m) { bstar = b; break; } }
+        if (bstar >= 0 && bstar < 31) { Tn = lo + (double)(bstar + 1) * width; if (Tn > hi) Tn = hi; }
+    }
+    int64_t cnt = 0;
+    for (int64_t i = 0; i < *len; i++) if (q[i].live && q[i].gain <= Tn) cnt++;
+    if (cnt < m) Tn = hi;
+    int64_t out = 0;
+    for (int64_t i = 0; i < *len; i++) {
+        if (q[i].live && q[i].gain <= Tn) q[out++] = q[i];
+        else if (q[i].live) node_free(q[i].node);
+    }
+    *len = out; *live = out; *T = Tn;
+}
+
+int64_t orc_kbest2d_cutoff_pruned(int64_t k, int64_t n, int64_t numCol, int maximize, const double* C,
+                                  int64_t* c4rBest, int64_t* r4cBest, double* gainBest, double cutoff,
+                                  int64_t maxCol, int64_t* stats) {
+    for (int i = 0; i < 6; i++) stats[i] = 0;
+    CutState cs = {1, maximize, 0.0};
+    Work w;
+    work_init(&w, n);
+    Node* cur = node_new(n);
+    const double CDelta = make_safe_padded(&w, C, n, numCol, maximize);
+    if (root_solve(cur, &w, w.C, n, n, numCol)) { node_free(cur); work_free(&w); return 0; }
+    emit(cur, 0, n, numCol, c4rBest, r4cBest);
+    gainBest[0] = cur->gain;
+    if (!maximize) { cs.cutoffGain = gainBest[0] + cutoff; gainBest[0] = gainBest[0] + CDelta; }
+    else { cs.cutoffGain = gainBest[0] - cutoff; gainBest[0] = -gainBest[0] + CDelta; }
+    const int64_t cap = (k + 2 * maxCol + 8 + 32 + 31) / 32 * 32;
+    Slot* q = (Slot*)malloc(sizeof(Slot) * (size_t)(cap + numCol + 1));
+    int64_t len = 0, live = 0, trig = 0, sweep, result = -1;
+    double T = INFINITY;
+    for (sweep = 1; sweep < k; sweep++) {
+        const int64_t m = k - sweep;
+        if ((T == INFINITY) ? (live >= m) : (live - m >= trig)) {
+            stats[4]++; stats[5] += len;
+            model_tighten(q, &len, &live, &T, m);
+            trig = live - m + 8;
+        }
+        if (len + numCol > cap) { result = -2; break; }
+        const double limit = (T - cur->gain) + 1e-7 * (T + 1.0);
+        /* split (:455-532), every child searched under the limit */
+        const int64_t a = cur->activeCol;
+        memset(w.inScanPar, 0, (size_t)n);
+        for (int64_t c = a; c < n; c++) w.inScanPar[cur->row4col[c]] = 1;
+        for (int64_t c = a; c < numCol; c++) {
+            memcpy(w.inScan, w.inScanPar, (size_t)n);
+            if (c == a) memcpy(w.forb, cur->forb, (size_t)n);
+            else { memset(w.forb, 0, (size_t)n); w.forb[cur->row4col[c]] = 1; }
+            stats[0]++;
+            t_limit = limit;
+            Node* ch = child_solve(cur, &w, c, numCol, n);
+            const int abandoned = (ch->gain == -1 && t_limit_hit);
+            t_limit = INFINITY;
+            if (abandoned) stats[1]++;
+            if (ch->gain == -1 || cut_hyp(&cs, ch->gain)) node_free(ch);
+            else if (ch->gain > T) { stats[2]++; node_free(ch); }
+            else { stats[3]++; q[len].gain = ch->gain; q[len].node = ch; q[len].live = 1; len++; live++; }
+            w.inScanPar[cur->row4col[c]] = 0;
+        }
+        node_free(cur);
+        cur = NULL;
+        if (live == 0) break;
+        /* take the smallest; a second live entry with the same bits means only the reference's heap can order them */
+        int64_t best = -1;
+        for (int64_t i = 0; i < len; i++) if (q[i].live && (best < 0 || q[i].gain < q[best].gain)) best = i;
+        int tie = 0;
+        for (int64_t i = 0; i < len; i++) if (q[i].live && i != best && q[i].gain == q[best].gain) tie = 1;
+        if (tie) { result = -2; break; }
+        cur = q[best].node;
+        q[best].live = 0;
+        live--;
+        emit(cur, sweep, n, numCol, c4rBest, r4cBest);
+        gainBest[sweep] = cur->gain;
+        if (!maximize) {
+            gainBest[sweep] = gainBest[sweep] + CDelta;
+            if (gainBest[sweep] > gainBest[0] + cutoff) break;
+        } else {
+            gainBest[sweep] = -gainBest[sweep] + CDelta;
+            if (gainBest[sweep] < gainBest[0] - cutoff) break;
+        }
+    }
+    if (result != -2) result = sweep;
+    for (int64_t i = 0; i < len; i++) if (q[i].live) node_free(q[i].node);
+    if (cur) node_free(cur);
+    free(q);
+    work_free(&w);
+    return result;
 }
 
 void orc_last_counters(int64_t* pops, int64_t* childSolves, int64_t* dijkstraIters, int64_t* evaluations, int64_t* maxHeap) {
