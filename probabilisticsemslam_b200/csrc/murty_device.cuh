@@ -298,7 +298,7 @@ __device__ __forceinline__ int augment_from(const int startCol, const int numCol
         int ff = 0;
         PDA_ASTAT(3);
         if (FF && padPrev) { PDA_ASTAT(1); ff = fast_forward<R>(numColReal, sm, nd, vEff, uRow, cand, closest, delta, lane); if (ff) PDA_ASTAT(2); }
-        if (ff == 2) return 1;
+        if (ff == 2) { __syncwarp(); return 1; }
         if (ff == 0) {
             PDA_ASTAT(0);
             // lane-local first minimum (lower slot = lower row wins ties; NaN = already scanned), then the warp arg-min
@@ -308,9 +308,9 @@ __device__ __forceinline__ int augment_from(const int startCol, const int numCol
             for (int s = 1; s < R; ++s) if (cand[s] < best || best != best) { best = cand[s]; bs = s; }
             int mhi;
             warp_argmin(best, lane + 32 * bs, mhi, delta, closest);
-            if (mhi >= HI_INF) return 1;  // minVal == +inf (:197, :327): nothing finite is left
+            if (mhi >= HI_INF) { __syncwarp(); return 1; }  // minVal == +inf (:197, :327): nothing finite is left
         }
-        if (LIMIT && delta > limit) return 2;
+        if (LIMIT && delta > limit) { __syncwarp(); return 2; }  // (sync: the caller rewrites sm.c4r next; all lanes have read it)
         if (lane == 0) sm.spc[closest] = delta;
 #pragma unroll
         for (int s = 0; s < R; ++s)
@@ -538,6 +538,7 @@ PDA_PQ_LOOP
     const int w = __ffs(eqi) - 1;
     nodeOut = q.node[32 * grp + w];
     const unsigned long long rest = warp_min_u64((lane == w) ? PQ_EMPTY : kk);
+    __syncwarp();  // every lane has read the group minima and this group's keys before lane 0 rewrites them (racecheck)
     if (lane == 0) { q.key[32 * grp + w] = PQ_EMPTY; q.gmin[grp] = rest; }
     keyOut = kmin;
     return tie;
