@@ -121,3 +121,24 @@ def test_datfile_roundtrip(tmp_path):
     assert open(p).read().splitlines()[1] == "0.123457,2.000000"       # std::to_string: 6 decimals
     back = datfile.read_dat(p)
     assert np.isinf(back[0, 1]) and back[1, 0] == 0.123457
+
+
+def test_host_batch_argument_checks_run_before_any_device_work():
+    """pda_murty_batch_host validates the whole batch on the host (dimensions, offsets, nL + numCol == numRow) before it
+    touches a device: the same answers with or without a GPU."""
+    from probabilisticsemslam_b200 import _lib
+    lib = _lib.lib()
+    costs = np.zeros(10)
+    off = np.zeros(1, np.int64); poff = np.zeros(1, np.int64)
+    found = np.zeros(1, np.int32); probs = np.zeros(8)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    def call(nr, nc, nl, cost_off=0):
+        off[0] = cost_off
+        a, b, c = np.array([nr], np.int32), np.array([nc], np.int32), np.array([nl], np.int32)
+        return lib.pda_murty_batch_host(p(costs), p(off), p(a), p(b), 1, 5, 1, 42.0, 0, 0, None, None, None, None, None, p(found),
+                                        1, p(probs), p(poff), p(c), 0)
+    assert call(2, 3, 0) == -1 and b"numRow >= numCol" in lib.pda_last_error()      # more detections than rows
+    assert call(5, 2, 2) == -1 and b"nL + numCol" in lib.pda_last_error()           # rows are not landmarks + detections
+    assert call(5, 2, 3, cost_off=-4) == -1 and b"negative offset" in lib.pda_last_error()
+    assert lib.pda_murty_batch_host(p(costs), p(off), None, None, 1, 5, 1, 42.0, 0, 0, None, None, None, None, None, p(found),
+                                    1, p(probs), p(poff), None, 0) == -1           # NULL inputs
