@@ -193,7 +193,9 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the product has no CPU path; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # a bounded collective timeout: a stuck exchange ends the run with an error after five minutes instead of hanging it
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=300))
     lib = _lib.lib()
     n, k = args.problems, args.k
 
